@@ -1,0 +1,41 @@
+"""pytest configuration: the `gpu` marker and shared helpers.
+
+`-m "not gpu"` runs here on CPU (oracle pins, host logic, C-ABI symbol checks, gloo slab tests);
+`-m gpu` runs on a B200 and calls the CUDA path through the C-ABI only.
+"""
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+    config.addinivalue_line("markers", "slow: takes more than ~20 s on CPU")
+
+
+def pytest_collection_modifyitems(config, items):
+    """GPU tests are skipped (not failed) when no device is visible, e.g. in the build container."""
+    have_gpu = None
+    for item in items:
+        if "gpu" in item.keywords:
+            if have_gpu is None:
+                try:
+                    import torch
+
+                    have_gpu = torch.cuda.is_available()
+                except Exception:
+                    have_gpu = False
+            if not have_gpu:
+                item.add_marker(pytest.mark.skip(reason="no CUDA device visible"))
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
