@@ -1,0 +1,864 @@
+// lbm_engine.cu -- host side of liblbm_b200.so: the slab object behind an lbm_handle, the step
+// scheduler (what Solver::run's loop body becomes, reference include/LBMSolver.h:48-76), the halo
+// exchange (Grid::exchange_ghost_cells, include/LBMGrid.h:249-283 -> NCCL send/recv of the three
+// populations that cross each slab face), and the extern "C" entry points of include/lbm_b200.h.
+//
+// State convention.  After t >= 1 reference iterations buffer f[cur] holds
+// the POST-COLLISION populations f_next of iteration t-1 and f[cur^1] still holds the state the
+// last launch read.  Every reference observable is derived from those two buffers on demand
+// (lbm_kernels.cu: k_macros, k_export_f), so the hot kernels store nothing but populations.
+// The ghost ring of both buffers permanently holds what the reference's f_next ghosts hold from
+// its first exchange on: 0.0 in the W/E ghost columns at physical domain edges, the initial
+// equilibrium in the S/N ghost rows and the four corners; slab-interface ghost
+// columns are refreshed by the exchange every iteration.
+#include <algorithm>
+#include <climits>
+#include <cstdlib>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/lbm_b200.h"
+#include "lbm_cell.cuh"
+#include "lbm_kernels.cuh"
+#include "lbm_layout.h"
+#include "lbm_nccl.h"
+
+using namespace lbm;
+
+namespace {
+thread_local std::string g_create_error;
+constexpr int FORCE_SLOTS = 1024;
+}  // namespace
+
+struct lbm_solver {
+    lbm_params p{};
+    Layout L{};
+    int device = 0, rank = 0, world = 1;
+    int cyl_x = 0, cyl_y = 0, cyl_r = 0;
+    bool periodic_x = false, periodic_y = false;
+
+    cudaStream_t stream = nullptr, copy_stream = nullptr, comm_stream = nullptr;
+    cudaEvent_t ev_macros = nullptr, ev_snapshot = nullptr, ev_edge = nullptr, ev_comm = nullptr;
+    bool snapshot_pending = false;
+
+    double* f[2] = {nullptr, nullptr};
+    int cur = 0;
+    bool cur_is_next = false, prev_is_next = false, fresh = false, initialised = false;
+    int iter = 0;
+
+    std::vector<unsigned char> h_mask;  // padded, Layout indexing
+    unsigned char* d_mask = nullptr;
+    int2* d_ring = nullptr;
+    int n_ring = 0;
+    int2* d_solids = nullptr;
+    int n_solid = 0;
+    int n_ring_edge = 0, n_solid_edge = 0;  // leading entries that lie in columns 0 / lnx-1
+    Link* d_links = nullptr;
+    int n_links = 0;
+
+    double *d_rho = nullptr, *d_ux = nullptr, *d_uy = nullptr;
+    bool macros_valid = false;
+    double* d_scratch = nullptr;  // padded AoS staging for lbm_download_f / lbm_upload_f
+    unsigned long long* d_maxbits = nullptr;
+
+    int* d_first_bad = nullptr;
+    double* d_forces = nullptr;  // FORCE_SLOTS x {fx, fy}
+    struct Pending { int t, slot; };
+    std::vector<Pending> pending;
+    struct ForceRow { int t; double fx, fy; };
+    std::vector<ForceRow> force_log;
+
+    BcArgs bc{};
+    double init_u = 0.0;
+    int variant = BULK_VEC2;
+    bool overlap = true;
+
+    ncclComm_t comm = nullptr;
+    int west = -1, east = -1;  // neighbour ranks or -1
+
+    long long launches = 0;
+    std::vector<cudaEvent_t> bulk_events;  // pairs, only while per-kernel timing is on
+    bool time_bulk = false;
+
+    std::string err;
+};
+
+namespace {
+
+int fail(lbm_handle h, int code, const std::string& msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CU(h, expr)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e__ = (expr);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return fail(h, LBM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));        \
+    } while (0)
+
+#define NC(h, expr)                                                                                   \
+    do {                                                                                              \
+        ncclResult_t r__ = (expr);                                                                    \
+        if (r__ != ncclSuccess)                                                                       \
+            return fail(h, LBM_ERR_NCCL, std::string(#expr) + ": " + nccl_api().GetErrorString(r__)); \
+    } while (0)
+
+#define CHECK_H(h) \
+    if (!(h)) return fail(nullptr, LBM_ERR_INVALID, "null handle")
+
+StepArgs step_args(lbm_handle h, const double* src, double* dst, int bad_iter, int write) {
+    StepArgs a;
+    a.src = src;
+    a.dst = dst;
+    a.L = h->L;
+    a.tau_inv = 1.0 / h->p.tau;  // include/LBMSolver.h:85
+    a.Fx = h->p.body_force_x;
+    a.Fy = h->p.body_force_y;
+    a.forced = (a.Fx != 0.0 || a.Fy != 0.0) ? 1 : 0;
+    a.first_bad = h->d_first_bad;
+    a.bad_iter = bad_iter;
+    a.write = write;
+    return a;
+}
+
+ObserveArgs observe_args(lbm_handle h) {
+    ObserveArgs o;
+    o.cur = h->f[h->cur];
+    o.prev = h->f[h->cur ^ 1];
+    o.L = h->L;
+    o.mask = h->d_mask;
+    o.bc = h->bc;
+    o.cur_is_next = h->cur_is_next;
+    o.prev_is_next = h->prev_is_next;
+    o.fresh = h->fresh;
+    o.shear_wave = (h->p.flags & LBM_FLAG_SHEAR_WAVE_INIT) ? 1 : 0;
+    o.u0 = h->init_u;
+    return o;
+}
+
+// Geometry on the host: mask over the padded slab in GLOBAL coordinates (reference
+// include/LBMGrid.h:159-172), the solid list, the boundary-ring list and the momentum-exchange
+// link list (include/LBMIO.h:123-160; a link is owned by the slab that owns its fluid end, so
+// no link is lost at a slab face -- cf. SURVEY.md F8).
+int build_geometry(lbm_handle h) {
+    const Layout& L = h->L;
+    const bool cyl = !(h->p.flags & LBM_FLAG_NO_CYLINDER);
+    std::fill(h->h_mask.begin(), h->h_mask.end(), 0);
+    auto solid_global = [&](int gxg, int gyg) -> bool {
+        if (!cyl) return false;
+        if (h->periodic_x) gxg = ((gxg % L.gnx) + L.gnx) % L.gnx;
+        if (h->periodic_y) gyg = ((gyg % L.ny) + L.ny) % L.ny;
+        if (gxg < 0 || gxg >= L.gnx || gyg < 0 || gyg >= L.ny) return false;
+        const double dx = gxg - h->cyl_x;
+        const double dy = gyg - h->cyl_y;
+        const double dist_sq = dx * dx + dy * dy;
+        return dist_sq <= h->cyl_r * h->cyl_r;
+    };
+    std::vector<int2> solids, ring;
+    std::vector<Link> links;
+    for (int gx = 0; gx < L.lnx + 2; ++gx)
+        for (int y = -1; y <= L.ny; ++y) {
+            const bool s = solid_global(L.x_start + gx - 1, y);
+            h->h_mask[L.at(gx, y)] = s ? 1 : 0;
+            if (s && gx >= 1 && gx <= L.lnx && y >= 0 && y < L.ny) solids.push_back(make_int2(gx - 1, y));
+        }
+    // ring: fluid cells that get a boundary rule between pull and collide
+    {
+        std::vector<int2> cand;
+        if (h->bc.walls)
+            for (int x = 0; x < L.lnx; ++x) {
+                cand.push_back(make_int2(x, 0));
+                cand.push_back(make_int2(x, L.ny - 1));
+            }
+        for (int y = 0; y < L.ny; ++y) {
+            if (h->bc.inlet) cand.push_back(make_int2(0, y));
+            if (h->bc.outlet) cand.push_back(make_int2(L.lnx - 1, y));
+        }
+        std::sort(cand.begin(), cand.end(), [](const int2& a, const int2& b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
+        cand.erase(std::unique(cand.begin(), cand.end(), [](const int2& a, const int2& b) { return a.x == b.x && a.y == b.y; }),
+                   cand.end());
+        for (const int2& c : cand)
+            if (!h->h_mask[L.at(c.x + 1, c.y)]) ring.push_back(c);
+    }
+    // Cells of the two slab-edge columns go first in both lists: with a neighbouring slab they
+    // are fixed up before the halo leaves, ahead of the interior (see step_one).
+    auto edge_first = [&](std::vector<int2>& v) -> int {
+        auto mid = std::stable_partition(v.begin(), v.end(), [&](const int2& c) { return c.x == 0 || c.x == L.lnx - 1; });
+        return (int)(mid - v.begin());
+    };
+    h->n_ring_edge = edge_first(ring);
+    h->n_solid_edge = edge_first(solids);
+    // links, in the reference's (y, x, i) order over solid cells
+    for (int y = 0; y < L.ny; ++y)
+        for (int x = -1; x <= L.lnx; ++x) {
+            if (!h->h_mask[L.at(x + 1, y)]) continue;
+            for (int i = 1; i < Q; ++i) {
+                int fx = x - cxi(i), fy = y - cyi(i);
+                if (h->periodic_y) fy = ((fy % L.ny) + L.ny) % L.ny;
+                if (fx >= 0 && fx < L.lnx && fy >= 0 && fy < L.ny && !h->h_mask[L.at(fx + 1, fy)]) {
+                    Link l;
+                    l.off = (long long)i * L.plane + L.at(fx + 1, fy);
+                    l.cx2 = 2 * cxi(i);
+                    l.cy2 = 2 * cyi(i);
+                    links.push_back(l);
+                }
+            }
+        }
+    cudaFree(h->d_ring); cudaFree(h->d_solids); cudaFree(h->d_links);
+    h->d_ring = nullptr; h->d_solids = nullptr; h->d_links = nullptr;
+    h->n_ring = (int)ring.size();
+    h->n_solid = (int)solids.size();
+    h->n_links = (int)links.size();
+    CU(h, cudaMemcpyAsync(h->d_mask, h->h_mask.data(), h->h_mask.size(), cudaMemcpyHostToDevice, h->stream));
+    if (h->n_ring) {
+        CU(h, cudaMalloc(&h->d_ring, sizeof(int2) * ring.size()));
+        CU(h, cudaMemcpyAsync(h->d_ring, ring.data(), sizeof(int2) * ring.size(), cudaMemcpyHostToDevice, h->stream));
+    }
+    if (h->n_solid) {
+        CU(h, cudaMalloc(&h->d_solids, sizeof(int2) * solids.size()));
+        CU(h, cudaMemcpyAsync(h->d_solids, solids.data(), sizeof(int2) * solids.size(), cudaMemcpyHostToDevice, h->stream));
+    }
+    if (h->n_links) {
+        CU(h, cudaMalloc(&h->d_links, sizeof(Link) * links.size()));
+        CU(h, cudaMemcpyAsync(h->d_links, links.data(), sizeof(Link) * links.size(), cudaMemcpyHostToDevice, h->stream));
+    }
+    CU(h, cudaStreamSynchronize(h->stream));  // the host vectors die here
+    return LBM_OK;
+}
+
+int drain_forces(lbm_handle h) {
+    if (h->pending.empty()) return LBM_OK;
+    std::vector<double> tmp(2 * FORCE_SLOTS);
+    CU(h, cudaMemcpyAsync(tmp.data(), h->d_forces, sizeof(double) * 2 * FORCE_SLOTS, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    for (const auto& pd : h->pending) h->force_log.push_back({pd.t, tmp[2 * pd.slot], tmp[2 * pd.slot + 1]});
+    h->pending.clear();
+    return LBM_OK;
+}
+
+// Halo exchange of the freshly written buffer: interior column lnx -> east neighbour's W ghost
+// (populations 1,5,8 move in +x), interior column 1 -> west neighbour's E ghost (3,6,7).
+// Rows 0..ny-1 only: ghost-row/corner entries keep the initial equilibrium as in the 1-rank
+// reference.  A column of one population is contiguous, so there is no pack kernel.
+int exchange(lbm_handle h, double* buf, cudaStream_t s) {
+    if (h->world == 1 || (h->west < 0 && h->east < 0)) return LBM_OK;
+    const NcclApi& N = nccl_api();
+    const Layout& L = h->L;
+    static const int to_east[3] = {1, 5, 8}, to_west[3] = {3, 6, 7};
+    NC(h, N.GroupStart());
+    for (int k = 0; k < 3; ++k) {
+        if (h->east >= 0) {
+            NC(h, N.Send(buf + to_east[k] * L.plane + L.at(L.lnx, 0), L.ny, ncclDouble, h->east, h->comm, s));
+            NC(h, N.Recv(buf + to_west[k] * L.plane + L.at(L.lnx + 1, 0), L.ny, ncclDouble, h->east, h->comm, s));
+        }
+        if (h->west >= 0) {
+            NC(h, N.Send(buf + to_west[k] * L.plane + L.at(1, 0), L.ny, ncclDouble, h->west, h->comm, s));
+            NC(h, N.Recv(buf + to_east[k] * L.plane + L.at(0, 0), L.ny, ncclDouble, h->west, h->comm, s));
+        }
+    }
+    NC(h, N.GroupEnd());
+    return LBM_OK;
+}
+
+// One reference iteration (include/LBMSolver.h:49-58) as kernel launches.
+int step_one(lbm_handle h) {
+    const Layout& L = h->L;
+    const bool pull = h->cur_is_next;
+    double* dst = h->f[h->cur ^ 1];
+    StepArgs a = step_args(h, h->f[h->cur], dst, h->iter - 1, 1);
+    const bool multi = (h->west >= 0 || h->east >= 0);
+    const bool split = multi && h->overlap && L.lnx >= 4;
+
+    auto bulk = [&](int x0, int x1) -> cudaError_t {
+        if (h->time_bulk) {
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            cudaEventRecord(e0, h->stream);
+            cudaError_t r = launch_bulk(h->variant, pull, a, h->stream, x0, x1);
+            cudaEventRecord(e1, h->stream);
+            h->bulk_events.push_back(e0);
+            h->bulk_events.push_back(e1);
+            return r;
+        }
+        return launch_bulk(h->variant, pull, a, h->stream, x0, x1);
+    };
+
+    if (split) {
+        // Edge columns first, so that their halo can travel while the interior is computed.
+        // The previous exchange (comm stream) must have landed before the edges are pulled.
+        CU(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
+        CU(h, launch_bulk(BULK_VEC2, pull, a, h->stream, 0, 1));
+        CU(h, launch_bulk(BULK_VEC2, pull, a, h->stream, L.lnx - 1, L.lnx));
+        CU(h, launch_fixup(pull, a, h->bc, h->d_ring, h->n_ring_edge, h->d_solids, h->n_solid_edge, h->stream));
+        h->launches += 3;
+        CU(h, cudaEventRecord(h->ev_edge, h->stream));
+        CU(h, cudaStreamWaitEvent(h->comm_stream, h->ev_edge, 0));
+        int rc = exchange(h, dst, h->comm_stream);
+        if (rc) return rc;
+        CU(h, cudaEventRecord(h->ev_comm, h->comm_stream));
+        CU(h, bulk(1, L.lnx - 1));
+        CU(h, launch_fixup(pull, a, h->bc, h->d_ring + h->n_ring_edge, h->n_ring - h->n_ring_edge,
+                           h->d_solids + h->n_solid_edge, h->n_solid - h->n_solid_edge, h->stream));
+        h->launches += 2;
+    } else {
+        CU(h, bulk(0, L.lnx));
+        CU(h, launch_fixup(pull, a, h->bc, h->d_ring, h->n_ring, h->d_solids, h->n_solid, h->stream));
+        h->launches += 2;
+        if (multi) {
+            int rc = exchange(h, dst, h->stream);
+            if (rc) return rc;
+        }
+    }
+    if (h->periodic_x && h->world == 1) { CU(h, launch_wrap(dst, L, 1, 0, h->stream)); h->launches += 1; }
+    if (h->periodic_y) {
+        // ghost columns must be final before the rows (corners) are wrapped
+        if (split) CU(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
+        CU(h, launch_wrap(dst, L, 0, 1, h->stream));
+        h->launches += 1;
+    }
+
+    // IOManager::record_forces, include/LBMSolver.h:52-54: after collision, on output steps
+    if (h->p.output_frequency > 0 && h->iter % h->p.output_frequency == 0) {
+        if ((int)h->pending.size() >= FORCE_SLOTS) {
+            int rc = drain_forces(h);
+            if (rc) return rc;
+        }
+        const int slot = (int)h->pending.size();
+        CU(h, launch_forces(dst, h->d_links, h->n_links, h->d_forces + 2 * slot, h->stream));
+        h->launches += 1;
+        h->pending.push_back({h->iter, slot});
+    }
+
+    h->cur ^= 1;
+    h->prev_is_next = h->cur_is_next;
+    h->cur_is_next = true;
+    h->fresh = false;
+    h->macros_valid = false;
+    h->iter += 1;
+    return LBM_OK;
+}
+
+int ensure_macros(lbm_handle h) {
+    if (h->macros_valid) return LBM_OK;
+    const size_t n = (size_t)h->L.lnx * h->L.ny * sizeof(double);
+    if (!h->d_rho) {
+        CU(h, cudaMalloc(&h->d_rho, n));
+        CU(h, cudaMalloc(&h->d_ux, n));
+        CU(h, cudaMalloc(&h->d_uy, n));
+    }
+    if (h->snapshot_pending) CU(h, cudaStreamWaitEvent(h->stream, h->ev_snapshot, 0));
+    if (h->west >= 0 || h->east >= 0) CU(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
+    CU(h, launch_macros(observe_args(h), h->d_rho, h->d_ux, h->d_uy, h->stream));
+    h->launches += 1;
+    h->macros_valid = true;
+    return LBM_OK;
+}
+
+int ensure_scratch(lbm_handle h) {
+    if (h->d_scratch) return LBM_OK;
+    const size_t n = (size_t)(h->L.lnx + 2) * (h->L.ny + 2) * Q * sizeof(double);
+    CU(h, cudaMalloc(&h->d_scratch, n));
+    return LBM_OK;
+}
+
+// Grid::check_stability of the CURRENT f_current (the last iteration's check), which the fused
+// kernels would only see one launch later: a store-less pass of the same kernels.
+int check_pending(lbm_handle h) {
+    if (!h->cur_is_next) return LBM_OK;
+    if (h->west >= 0 || h->east >= 0) CU(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
+    StepArgs a = step_args(h, h->f[h->cur], h->f[h->cur ^ 1], h->iter - 1, 0);
+    CU(h, launch_bulk(BULK_VEC2, true, a, h->stream, 0, h->L.lnx));
+    CU(h, launch_fixup(true, a, h->bc, h->d_ring, h->n_ring, nullptr, 0, h->stream));
+    h->launches += 2;
+    return LBM_OK;
+}
+
+int read_first_bad(lbm_handle h, int* out) {
+    int v = INT_MAX;
+    CU(h, cudaMemcpyAsync(&v, h->d_first_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    *out = v;
+    return LBM_OK;
+}
+
+int create_common(const lbm_params* p, int device, int rank, int world, const void* uid, lbm_handle* out) {
+    if (!p || !out) return fail(nullptr, LBM_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (p->nx <= 0 || p->ny <= 0) return fail(nullptr, LBM_ERR_INVALID, "nx and ny must be positive");
+    if (!(p->tau > 0.5)) return fail(nullptr, LBM_ERR_INVALID, "tau must exceed 0.5");
+    if (world < 1 || rank < 0 || rank >= world) return fail(nullptr, LBM_ERR_INVALID, "bad rank/world");
+    if (p->nx % world != 0)  // include/LBMGrid.h:358 requires divisibility too
+        return fail(nullptr, LBM_ERR_INVALID, "nx must be divisible by the number of slabs");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, LBM_ERR_CUDA, std::string("no CUDA device: liblbm_b200 has no CPU path (") +
+                                               cudaGetErrorString(e) + ")");
+    if (device < 0 || device >= ndev) return fail(nullptr, LBM_ERR_INVALID, "device index out of range");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, LBM_ERR_CUDA, cudaGetErrorString(e));
+
+    lbm_handle h = new lbm_solver();
+    h->p = *p;
+    h->device = device;
+    h->rank = rank;
+    h->world = world;
+    h->periodic_x = (p->flags & LBM_FLAG_PERIODIC_X) != 0;
+    h->periodic_y = (p->flags & LBM_FLAG_PERIODIC_Y) != 0;
+    const int lnx = p->nx / world;
+    h->L = Layout::make(lnx, p->ny, p->nx, rank * lnx);
+    // include/LBMConfig.h:61-65
+    h->cyl_x = static_cast<int>(p->cylinder_x * p->nx);
+    h->cyl_y = static_cast<int>(p->cylinder_y * p->ny);
+    h->cyl_r = static_cast<int>(p->cylinder_radius * p->ny);
+    h->bc.u_in = p->inlet_velocity;
+    h->bc.inlet = (!h->periodic_x && rank == 0) ? 1 : 0;
+    h->bc.outlet = (!h->periodic_x && rank == world - 1) ? 1 : 0;
+    h->bc.walls = h->periodic_y ? 0 : 1;
+    equilibrium_init(1.0, 0.0, 0.0, h->bc.w);
+    equilibrium_init(1.0, p->inlet_velocity, 0.0, h->bc.e);
+    h->init_u = p->inlet_velocity;
+    if (const char* v = std::getenv("LBM_B200_VARIANT")) h->variant = std::atoi(v);
+    if (const char* v = std::getenv("LBM_B200_OVERLAP")) h->overlap = std::atoi(v) != 0;
+    if (world > 1) {
+        h->west = rank > 0 ? rank - 1 : (h->periodic_x ? world - 1 : -1);
+        h->east = rank < world - 1 ? rank + 1 : (h->periodic_x ? 0 : -1);
+    }
+
+    auto bail = [&](int code, const std::string& m) {
+        g_create_error = m;
+        lbm_destroy(h);
+        return code;
+    };
+#define CUC(expr)                                                                              \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return bail(e__ == cudaErrorMemoryAllocation ? LBM_ERR_NOMEM : LBM_ERR_CUDA,       \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                  \
+    } while (0)
+    int lo = 0, hi = 0;
+    CUC(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUC(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, lo));
+    CUC(cudaStreamCreateWithPriority(&h->copy_stream, cudaStreamNonBlocking, lo));
+    CUC(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, hi));
+    CUC(cudaEventCreateWithFlags(&h->ev_macros, cudaEventDisableTiming));
+    CUC(cudaEventCreateWithFlags(&h->ev_snapshot, cudaEventDisableTiming));
+    CUC(cudaEventCreateWithFlags(&h->ev_edge, cudaEventDisableTiming));
+    CUC(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
+    const size_t fbytes = (size_t)h->L.plane * Q * sizeof(double);
+    CUC(cudaMalloc(&h->f[0], fbytes));
+    CUC(cudaMalloc(&h->f[1], fbytes));
+    CUC(cudaMemsetAsync(h->f[0], 0, fbytes, h->stream));
+    CUC(cudaMemsetAsync(h->f[1], 0, fbytes, h->stream));
+    h->h_mask.assign((size_t)h->L.cells_padded(), 0);
+    CUC(cudaMalloc(&h->d_mask, h->h_mask.size()));
+    CUC(cudaMemsetAsync(h->d_mask, 0, h->h_mask.size(), h->stream));
+    CUC(cudaMalloc(&h->d_first_bad, sizeof(int)));
+    CUC(cudaMalloc(&h->d_forces, sizeof(double) * 2 * FORCE_SLOTS));
+    CUC(cudaMalloc(&h->d_maxbits, sizeof(unsigned long long)));
+    const int big = INT_MAX;
+    CUC(cudaMemcpyAsync(h->d_first_bad, &big, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CUC(cudaStreamSynchronize(h->stream));
+    CUC(cudaEventRecord(h->ev_comm, h->comm_stream));
+#undef CUC
+    if (world > 1) {
+        const NcclApi& N = nccl_api();
+        if (!N.ok) return bail(LBM_ERR_NCCL, std::string("NCCL unavailable: ") + N.why);
+        if (!uid) return bail(LBM_ERR_INVALID, "nccl_unique_id is required when world > 1");
+        ncclUniqueId id;
+        static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+        std::memcpy(&id, uid, sizeof(id));
+        ncclResult_t r = N.CommInitRank(&h->comm, world, id, rank);
+        if (r != ncclSuccess) return bail(LBM_ERR_NCCL, std::string("ncclCommInitRank: ") + N.GetErrorString(r));
+    }
+    // ring list etc. for an obstacle-free domain; lbm_setup_geometry adds the cylinder
+    {
+        const int keep = h->p.flags;
+        h->p.flags |= LBM_FLAG_NO_CYLINDER;
+        int rc = build_geometry(h);
+        h->p.flags = keep;
+        if (rc) {
+            std::string m = h->err;
+            return bail(rc, m);
+        }
+    }
+    *out = h;
+    return LBM_OK;
+}
+
+}  // namespace
+
+// ============================================================================================
+extern "C" {
+
+int lbm_device_count(int* n) {
+    if (!n) return LBM_ERR_INVALID;
+    cudaError_t e = cudaGetDeviceCount(n);
+    if (e != cudaSuccess) {
+        *n = 0;
+        return fail(nullptr, LBM_ERR_CUDA, cudaGetErrorString(e));
+    }
+    return LBM_OK;
+}
+
+int lbm_create(const lbm_params* p, int device, lbm_handle* out) { return create_common(p, device, 0, 1, nullptr, out); }
+
+int lbm_create_slab(const lbm_params* p, int device, int rank, int world, const void* uid, lbm_handle* out) {
+    return create_common(p, device, rank, world, uid, out);
+}
+
+int lbm_nccl_unique_id(void* out128) {
+    if (!out128) return LBM_ERR_INVALID;
+    const NcclApi& N = nccl_api();
+    if (!N.ok) return fail(nullptr, LBM_ERR_NCCL, std::string("NCCL unavailable: ") + N.why);
+    ncclUniqueId id;
+    ncclResult_t r = N.GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(nullptr, LBM_ERR_NCCL, N.GetErrorString(r));
+    std::memcpy(out128, &id, sizeof(id));
+    return LBM_OK;
+}
+
+int lbm_destroy(lbm_handle h) {
+    if (!h) return LBM_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+    if (h->comm) nccl_api().CommDestroy(h->comm);
+    for (cudaEvent_t e : h->bulk_events) cudaEventDestroy(e);
+    cudaFree(h->f[0]); cudaFree(h->f[1]); cudaFree(h->d_mask); cudaFree(h->d_ring); cudaFree(h->d_solids);
+    cudaFree(h->d_links); cudaFree(h->d_rho); cudaFree(h->d_ux); cudaFree(h->d_uy); cudaFree(h->d_scratch);
+    cudaFree(h->d_first_bad); cudaFree(h->d_forces); cudaFree(h->d_maxbits);
+    if (h->ev_macros) cudaEventDestroy(h->ev_macros);
+    if (h->ev_snapshot) cudaEventDestroy(h->ev_snapshot);
+    if (h->ev_edge) cudaEventDestroy(h->ev_edge);
+    if (h->ev_comm) cudaEventDestroy(h->ev_comm);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+    delete h;
+    return LBM_OK;
+}
+
+const char* lbm_last_error(lbm_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int lbm_get_info(lbm_handle h, lbm_info* o) {
+    CHECK_H(h);
+    if (!o) return fail(h, LBM_ERR_INVALID, "null info");
+    o->abi_version = LBM_B200_ABI_VERSION;
+    o->global_nx = h->p.nx; o->global_ny = h->p.ny;
+    o->local_nx = h->L.lnx; o->local_ny = h->L.ny;
+    o->x_start = h->L.x_start; o->y_start = 0;
+    o->rank = h->rank; o->world = h->world; o->device = h->device;
+    o->cyl_x = h->cyl_x; o->cyl_y = h->cyl_y; o->cyl_r = h->cyl_r;
+    o->solid_cells = h->n_solid; o->links = h->n_links; o->iteration = h->iter;
+    o->bytes_per_buffer = (int64_t)h->L.plane * Q * (int64_t)sizeof(double);
+    o->row_pitch = h->L.PY;
+    o->kernel_variant = h->variant;
+    return LBM_OK;
+}
+
+int lbm_setup_geometry(lbm_handle h, int* solid_count) {
+    CHECK_H(h);
+    CU(h, cudaSetDevice(h->device));
+    int rc = build_geometry(h);
+    if (rc) return rc;
+    if (solid_count) *solid_count = h->n_solid;
+    return LBM_OK;
+}
+
+int lbm_initialise(lbm_handle h, double inlet_u) {
+    CHECK_H(h);
+    CU(h, cudaSetDevice(h->device));
+    h->init_u = inlet_u;
+    equilibrium_init(1.0, inlet_u, 0.0, h->bc.e);
+    const int wz = (!h->periodic_x && h->rank == 0) ? 1 : 0;
+    const int ez = (!h->periodic_x && h->rank == h->world - 1) ? 1 : 0;
+    const int sw = (h->p.flags & LBM_FLAG_SHEAR_WAVE_INIT) ? 1 : 0;
+    CU(h, launch_init(h->f[0], h->f[1], h->L, h->d_mask, h->bc, wz, ez, sw, inlet_u, h->stream));
+    h->launches += 1;
+    const int big = INT_MAX;
+    CU(h, cudaMemcpyAsync(h->d_first_bad, &big, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->cur = 0;
+    h->cur_is_next = false;
+    h->prev_is_next = false;
+    h->fresh = true;
+    h->initialised = true;
+    h->iter = 0;
+    h->macros_valid = false;
+    h->pending.clear();
+    h->force_log.clear();
+    return LBM_OK;
+}
+
+int lbm_step(lbm_handle h, int n_steps) {
+    CHECK_H(h);
+    if (!h->initialised) return fail(h, LBM_ERR_INVALID, "lbm_initialise or lbm_upload_f first");
+    if (n_steps < 0) return fail(h, LBM_ERR_INVALID, "n_steps < 0");
+    CU(h, cudaSetDevice(h->device));
+    for (int k = 0; k < n_steps; ++k) {
+        int rc = step_one(h);
+        if (rc) return rc;
+    }
+    return LBM_OK;
+}
+
+int lbm_sync(lbm_handle h) {
+    CHECK_H(h);
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaStreamSynchronize(h->comm_stream));
+    CU(h, cudaStreamSynchronize(h->copy_stream));
+    return LBM_OK;
+}
+
+int lbm_run(lbm_handle h, int n_steps, double* rows, int max_rows, int* n_rows, int* unstable_at) {
+    CHECK_H(h);
+    if (unstable_at) *unstable_at = -1;
+    if (n_rows) *n_rows = 0;
+    const int t0 = h->iter;
+    const size_t log0 = h->force_log.size();
+    int bad = INT_MAX;
+    // Launch in chunks; look at the stability flag between chunks so that a blown-up run stops
+    // within one chunk instead of grinding through NaNs for 120 000 steps.
+    const int chunk = h->p.output_frequency > 0 ? (h->p.output_frequency < 64 ? 64 : h->p.output_frequency) : 256;
+    int done = 0;
+    while (done < n_steps) {
+        const int n = (n_steps - done < chunk) ? (n_steps - done) : chunk;
+        int rc = lbm_step(h, n);
+        if (rc) return rc;
+        done += n;
+        rc = drain_forces(h);
+        if (rc) return rc;
+        rc = read_first_bad(h, &bad);
+        if (rc) return rc;
+        if (bad != INT_MAX) break;
+    }
+    if (bad == INT_MAX) {  // the last iteration's own check
+        int rc = check_pending(h);
+        if (rc) return rc;
+        rc = read_first_bad(h, &bad);
+        if (rc) return rc;
+    }
+    const int bad_iter = (bad == INT_MAX) ? -1 : bad;
+    // rows the reference would have written: output steps t <= failing iteration
+    int k = 0;
+    const double D_ref = 2.0 * h->cyl_r;                                           // include/LBMIO.h:174
+    const double q_ref = 0.5 * 1.0 * h->p.inlet_velocity * h->p.inlet_velocity * D_ref;  // :176
+    for (size_t r = log0; r < h->force_log.size(); ++r) {
+        const auto& fr = h->force_log[r];
+        if (fr.t < t0) continue;
+        if (bad_iter >= 0 && fr.t > bad_iter) break;
+        if (rows && k < max_rows) {
+            double* o = rows + 5 * (size_t)k;
+            o[0] = fr.t; o[1] = fr.fx; o[2] = fr.fy;
+            o[3] = (q_ref > 1e-12) ? fr.fx / q_ref : 0.0;  // :177-178
+            o[4] = (q_ref > 1e-12) ? fr.fy / q_ref : 0.0;
+        }
+        ++k;
+    }
+    if (n_rows) *n_rows = k;
+    if (unstable_at) *unstable_at = bad_iter;
+    return LBM_OK;
+}
+
+int lbm_get_forces(lbm_handle h, double* fx, double* fy) {
+    CHECK_H(h);
+    CU(h, cudaSetDevice(h->device));
+    int rc = drain_forces(h);
+    if (rc) return rc;
+    CU(h, launch_forces(h->f[h->cur], h->d_links, h->n_links, h->d_forces, h->stream));
+    h->launches += 1;
+    double v[2];
+    CU(h, cudaMemcpyAsync(v, h->d_forces, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (fx) *fx = v[0];
+    if (fy) *fy = v[1];
+    return LBM_OK;
+}
+
+int lbm_check_stability(lbm_handle h, int* ok, int* first_bad_step) {
+    CHECK_H(h);
+    CU(h, cudaSetDevice(h->device));
+    int rc = check_pending(h);
+    if (rc) return rc;
+    int bad = INT_MAX;
+    rc = read_first_bad(h, &bad);
+    if (rc) return rc;
+    if (ok) *ok = (bad == INT_MAX) ? 1 : 0;
+    if (first_bad_step) *first_bad_step = (bad == INT_MAX) ? -1 : bad;
+    return LBM_OK;
+}
+
+int lbm_max_velocity(lbm_handle h, double* out) {
+    CHECK_H(h);
+    CU(h, cudaSetDevice(h->device));
+    int rc = ensure_macros(h);
+    if (rc) return rc;
+    CU(h, launch_maxvel(h->d_ux, h->d_uy, (long long)h->L.lnx * h->L.ny, h->d_maxbits, h->stream));
+    h->launches += 1;
+    unsigned long long bits = 0;
+    CU(h, cudaMemcpyAsync(&bits, h->d_maxbits, sizeof(bits), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    double m;
+    std::memcpy(&m, &bits, sizeof(m));
+    if (out) *out = std::sqrt(m);  // include/LBMGrid.h:343
+    return LBM_OK;
+}
+
+int lbm_download_f(lbm_handle h, int which, double* aos) {
+    CHECK_H(h);
+    if (!aos || (which != LBM_F_CURRENT && which != LBM_F_NEXT)) return fail(h, LBM_ERR_INVALID, "bad argument");
+    CU(h, cudaSetDevice(h->device));
+    int rc = ensure_scratch(h);
+    if (rc) return rc;
+    if (h->west >= 0 || h->east >= 0) CU(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
+    CU(h, launch_export_f(observe_args(h), which, h->d_scratch, h->stream));
+    h->launches += 1;
+    const size_t n = (size_t)(h->L.lnx + 2) * (h->L.ny + 2) * Q * sizeof(double);
+    CU(h, cudaMemcpyAsync(aos, h->d_scratch, n, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return LBM_OK;
+}
+
+int lbm_download_macros(lbm_handle h, double* rho, double* ux, double* uy) {
+    CHECK_H(h);
+    CU(h, cudaSetDevice(h->device));
+    int rc = ensure_macros(h);
+    if (rc) return rc;
+    const size_t n = (size_t)h->L.lnx * h->L.ny * sizeof(double);
+    if (rho) CU(h, cudaMemcpyAsync(rho, h->d_rho, n, cudaMemcpyDeviceToHost, h->stream));
+    if (ux) CU(h, cudaMemcpyAsync(ux, h->d_ux, n, cudaMemcpyDeviceToHost, h->stream));
+    if (uy) CU(h, cudaMemcpyAsync(uy, h->d_uy, n, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return LBM_OK;
+}
+
+int lbm_download_solid(lbm_handle h, unsigned char* mask) {
+    CHECK_H(h);
+    if (!mask) return fail(h, LBM_ERR_INVALID, "null mask");
+    for (int y = 0; y < h->L.ny; ++y)
+        for (int x = 0; x < h->L.lnx; ++x) mask[(size_t)y * h->L.lnx + x] = h->h_mask[h->L.at(x + 1, y)];
+    return LBM_OK;
+}
+
+int lbm_upload_f(lbm_handle h, const double* aos, int iteration) {
+    CHECK_H(h);
+    if (!aos || iteration < 0) return fail(h, LBM_ERR_INVALID, "bad argument");
+    CU(h, cudaSetDevice(h->device));
+    int rc = ensure_scratch(h);
+    if (rc) return rc;
+    rc = drain_forces(h);
+    if (rc) return rc;
+    const size_t n = (size_t)(h->L.lnx + 2) * (h->L.ny + 2) * Q * sizeof(double);
+    CU(h, cudaMemcpyAsync(h->d_scratch, aos, n, cudaMemcpyHostToDevice, h->stream));
+    h->cur = 0;
+    CU(h, launch_import_f(h->d_scratch, h->f[0], h->L, h->stream));
+    const int wz = (!h->periodic_x && h->rank == 0) ? 1 : 0;
+    const int ez = (!h->periodic_x && h->rank == h->world - 1) ? 1 : 0;
+    CU(h, launch_reset_ghosts(h->f[0], h->L, h->bc, wz, ez, h->stream));
+    CU(h, launch_reset_ghosts(h->f[1], h->L, h->bc, wz, ez, h->stream));
+    h->launches += 3;
+    const int big = INT_MAX;
+    CU(h, cudaMemcpyAsync(h->d_first_bad, &big, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->cur_is_next = false;
+    h->prev_is_next = false;
+    h->fresh = false;
+    h->initialised = true;
+    h->iter = iteration;
+    h->macros_valid = false;
+    return LBM_OK;
+}
+
+int lbm_snapshot_begin(lbm_handle h, double* rho, double* ux, double* uy) {
+    CHECK_H(h);
+    CU(h, cudaSetDevice(h->device));
+    int rc = ensure_macros(h);
+    if (rc) return rc;
+    CU(h, cudaEventRecord(h->ev_macros, h->stream));
+    CU(h, cudaStreamWaitEvent(h->copy_stream, h->ev_macros, 0));
+    const size_t n = (size_t)h->L.lnx * h->L.ny * sizeof(double);
+    if (rho) CU(h, cudaMemcpyAsync(rho, h->d_rho, n, cudaMemcpyDeviceToHost, h->copy_stream));
+    if (ux) CU(h, cudaMemcpyAsync(ux, h->d_ux, n, cudaMemcpyDeviceToHost, h->copy_stream));
+    if (uy) CU(h, cudaMemcpyAsync(uy, h->d_uy, n, cudaMemcpyDeviceToHost, h->copy_stream));
+    CU(h, cudaEventRecord(h->ev_snapshot, h->copy_stream));
+    h->snapshot_pending = true;
+    return LBM_OK;
+}
+
+int lbm_snapshot_wait(lbm_handle h) {
+    CHECK_H(h);
+    CU(h, cudaSetDevice(h->device));
+    if (h->snapshot_pending) {
+        CU(h, cudaEventSynchronize(h->ev_snapshot));
+        h->snapshot_pending = false;
+    }
+    return LBM_OK;
+}
+
+int lbm_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return LBM_ERR_INVALID;
+    cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(nullptr, e == cudaErrorMemoryAllocation ? LBM_ERR_NOMEM : LBM_ERR_CUDA, cudaGetErrorString(e));
+    return LBM_OK;
+}
+
+int lbm_host_free(void* ptr) {
+    cudaError_t e = cudaFreeHost(ptr);
+    if (e != cudaSuccess) return fail(nullptr, LBM_ERR_CUDA, cudaGetErrorString(e));
+    return LBM_OK;
+}
+
+int lbm_time_steps(lbm_handle h, int n_steps, int per_kernel, float* ms_total, float* ms_bulk, int* launches) {
+    CHECK_H(h);
+    if (!h->initialised) return fail(h, LBM_ERR_INVALID, "lbm_initialise first");
+    CU(h, cudaSetDevice(h->device));
+    cudaEvent_t e0, e1;
+    CU(h, cudaEventCreate(&e0));
+    CU(h, cudaEventCreate(&e1));
+    const long long l0 = h->launches;
+    h->time_bulk = per_kernel != 0;
+    CU(h, cudaStreamSynchronize(h->comm_stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaEventRecord(e0, h->stream));
+    int rc = lbm_step(h, n_steps);
+    h->time_bulk = false;
+    if (rc) return rc;
+    if (h->west >= 0 || h->east >= 0) CU(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
+    CU(h, cudaEventRecord(e1, h->stream));
+    CU(h, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(h, cudaEventElapsedTime(&ms, e0, e1));
+    if (ms_total) *ms_total = ms;
+    float sum = 0.f;
+    for (size_t k = 0; k + 1 < h->bulk_events.size(); k += 2) {
+        float m = 0.f;
+        cudaEventElapsedTime(&m, h->bulk_events[k], h->bulk_events[k + 1]);
+        sum += m;
+        cudaEventDestroy(h->bulk_events[k]);
+        cudaEventDestroy(h->bulk_events[k + 1]);
+    }
+    h->bulk_events.clear();
+    if (ms_bulk) *ms_bulk = sum;
+    if (launches) *launches = (int)(h->launches - l0);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return LBM_OK;
+}
+
+int lbm_set_kernel_variant(lbm_handle h, int variant) {
+    CHECK_H(h);
+    if (variant < 0 || variant > 2) return fail(h, LBM_ERR_INVALID, "variant must be 0, 1 or 2");
+    h->variant = variant;
+    return LBM_OK;
+}
+
+}  // extern "C"

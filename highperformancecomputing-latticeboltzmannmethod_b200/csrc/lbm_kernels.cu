@@ -1,0 +1,516 @@
+// lbm_kernels.cu -- sm_100a kernels of the D2Q9 collide-stream path (all but the TMA-pipelined bulk
+// kernel, which lives in lbm_bulk_tma.cu).  Compiled with -fmad=false: see lbm_cell.cuh.
+//
+// Per iteration t >= 1 the engine launches, on one stream:
+//   k_bulk_*   every interior cell: new(c) = collide(pull(old))          branch-free, HBM-bound
+//   k_fixup    O(nx + ny + solids) cells: redo ring cells with the boundary rules between pull
+//              and collide; reset solid cells to w                        list-driven
+//   k_forces   output steps only: link-list momentum-exchange reduction
+// which together equal collision_step + exchange_ghost_cells + streaming_step +
+// apply_boundary_conditions + check_stability of the reference (include/LBMSolver.h:48-64) with
+// the state kept as post-collision populations.
+#include <cstdint>
+
+#include "lbm_cell.cuh"
+#include "lbm_kernels.cuh"
+
+namespace lbm {
+
+namespace {
+
+template <bool PULL>
+__device__ __forceinline__ void load_cell(const double* __restrict__ src, const Layout& L, int gx, int y,
+                                          double f[Q]) {
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+        const int dx = PULL ? cxi(i) : 0, dy = PULL ? cyi(i) : 0;
+        f[i] = __ldg(src + i * L.plane + L.at(gx - dx, y - dy));
+    }
+}
+
+__device__ __forceinline__ void store_cell(double* __restrict__ dst, const Layout& L, int gx, int y,
+                                           const double f[Q]) {
+#pragma unroll
+    for (int i = 0; i < Q; ++i) dst[i * L.plane + L.at(gx, y)] = f[i];
+}
+
+template <bool FORCED>
+__device__ __forceinline__ void collide_cell(double f[Q], double tau_inv, double Fx, double Fy) {
+    const Moments m = moments(f);
+    if (FORCED)
+        bgk_forced(f, m, tau_inv, Fx, Fy, f);
+    else
+        bgk(f, m, tau_inv, f);
+}
+
+__device__ __forceinline__ bool any_unstable(const double f[Q]) {
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < Q; ++i) bad |= unstable_value(f[i]);
+    return bad;
+}
+
+// The reference's boundary rules in its serial order (include/LBMSolver.h:153-236):
+// bottom row, top row, inlet column, outlet column.  x, y are slab-interior coordinates.
+__device__ __forceinline__ void apply_bc(double f[Q], int x, int y, const Layout& L, const BcArgs& b,
+                                         double& rho_bc, double& u_out) {
+    if (b.walls && y == 0) wall_bottom(f);
+    if (b.walls && y == L.ny - 1) wall_top(f);
+    if (b.inlet && x == 0) rho_bc = zou_he_inlet(f, b.u_in);
+    if (b.outlet && x == L.lnx - 1) u_out = zou_he_outlet(f);
+}
+
+// ------------------------------------------------------------------------------------------
+// Bulk kernel, variant 0: one cell per thread.  Correct for any ny; the baseline the other
+// variants are measured against.
+template <bool PULL, bool FORCED>
+__global__ void __launch_bounds__(256) k_bulk_scalar(StepArgs a, int x_begin, int x_end) {
+    const Layout& L = a.L;
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= L.ny) return;
+    bool bad = false;
+    for (int x = x_begin + blockIdx.y; x < x_end; x += gridDim.y) {
+        double f[Q];
+        load_cell<PULL>(a.src, L, x + 1, y, f);
+        if (PULL) bad |= any_unstable(f);
+        collide_cell<FORCED>(f, a.tau_inv, a.Fx, a.Fy);
+        if (a.write) store_cell(a.dst, L, x + 1, y, f);
+    }
+    if (bad) atomicMin(a.first_bad, a.bad_iter);
+}
+
+// Bulk kernel, variant 1: two y-adjacent cells per thread.  The three populations that do not
+// move in y (0, 1, 3) and all nine stores are 128-bit accesses; the six y-shifted pulls are
+// misaligned by one element and use two 64-bit loads each (the second one hits the lines the
+// first one brought into L1).  Requires even ny.
+template <bool PULL, bool FORCED>
+__global__ void __launch_bounds__(128) k_bulk_vec2(StepArgs a, int x_begin, int x_end) {
+    const Layout& L = a.L;
+    const int y = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (y >= L.ny) return;
+    bool bad = false;
+    for (int x = x_begin + blockIdx.y; x < x_end; x += gridDim.y) {
+        const int gx = x + 1;
+        double fa[Q], fb[Q];
+#pragma unroll
+        for (int i = 0; i < Q; ++i) {
+            const int dx = PULL ? cxi(i) : 0, dy = PULL ? cyi(i) : 0;
+            const double* p = a.src + i * L.plane + L.at(gx - dx, y - dy);
+            if (dy == 0) {
+                const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+                fa[i] = v.x;
+                fb[i] = v.y;
+            } else {
+                fa[i] = __ldg(p);
+                fb[i] = __ldg(p + 1);
+            }
+        }
+        if (PULL) bad |= any_unstable(fa) | any_unstable(fb);
+        collide_cell<FORCED>(fa, a.tau_inv, a.Fx, a.Fy);
+        collide_cell<FORCED>(fb, a.tau_inv, a.Fx, a.Fy);
+        if (a.write) {
+#pragma unroll
+            for (int i = 0; i < Q; ++i)
+                *reinterpret_cast<double2*>(a.dst + i * L.plane + L.at(gx, y)) = make_double2(fa[i], fb[i]);
+        }
+    }
+    if (bad) atomicMin(a.first_bad, a.bad_iter);
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_fixup(StepArgs a, BcArgs b, int pull, const int2* __restrict__ ring,
+                                               int n_ring, const int2* __restrict__ solids, int n_solid) {
+    const Layout& L = a.L;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n_ring) {
+        const int2 c = ring[idx];
+        double f[Q];
+        load_cell<true>(a.src, L, c.x + 1, c.y, f);
+        double rho_bc, u_out;
+        apply_bc(f, c.x, c.y, L, b, rho_bc, u_out);
+        if (any_unstable(f)) atomicMin(a.first_bad, a.bad_iter);
+        if (a.forced)
+            collide_cell<true>(f, a.tau_inv, a.Fx, a.Fy);
+        else
+            collide_cell<false>(f, a.tau_inv, 0.0, 0.0);
+        if (a.write) store_cell(a.dst, L, c.x + 1, c.y, f);
+    } else if (idx - n_ring < n_solid) {
+        // Solid cells never collide (include/LBMSolver.h:92): f_next keeps eq(1,0,0) for ever and
+        // the fluid neighbours simply pull those constants.
+        const int2 c = solids[idx - n_ring];
+        if (a.write) store_cell(a.dst, L, c.x + 1, c.y, b.w);
+    }
+    (void)pull;
+}
+
+// ------------------------------------------------------------------------------------------
+// Momentum exchange: F = sum over links 2 c_i f_next(fluid, i)  (include/LBMIO.h:153-158).
+// One block, fixed reduction tree => run-to-run deterministic.
+__global__ void __launch_bounds__(256) k_forces(const double* __restrict__ f, const Link* __restrict__ links,
+                                                int n_links, double* __restrict__ out) {
+    double fx = 0.0, fy = 0.0;
+    for (int k = threadIdx.x; k < n_links; k += blockDim.x) {
+        const Link l = links[k];
+        const double v = f[l.off];
+        fx += (double)l.cx2 * v;
+        fy += (double)l.cy2 * v;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        fx += __shfl_down_sync(0xffffffffu, fx, s);
+        fy += __shfl_down_sync(0xffffffffu, fy, s);
+    }
+    __shared__ double sx[8], sy[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        sx[warp] = fx;
+        sy[warp] = fy;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tx = 0.0, ty = 0.0;
+        for (int w = 0; w < 8; ++w) {
+            tx += sx[w];
+            ty += sy[w];
+        }
+        out[0] = tx;
+        out[1] = ty;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Periodic extensions: copy the opposite interior edge into the ghost ring.
+__global__ void k_wrap(double* __restrict__ f, Layout L, int wrap_x, int wrap_y) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    double* p = f + i * L.plane;
+    if (wrap_x && t < L.ny) {
+        p[L.at(0, t)] = p[L.at(L.lnx, t)];
+        p[L.at(L.lnx + 1, t)] = p[L.at(1, t)];
+    }
+    if (wrap_y && t < L.lnx + 2) {
+        // columns incl. ghost columns: after the x wrap above has been made visible by a
+        // previous launch (the engine launches x then y) the corners come out right.
+        p[L.at(t, -1)] = p[L.at(t, L.ny - 1)];
+        p[L.at(t, L.ny)] = p[L.at(t, 0)];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Initial state.  Every padded cell of both buffers = eq(1, u_in, 0) (include/LBMGrid.h:191-212),
+// solids = eq(1,0,0) (:229-242).  The W/E ghost columns at physical domain edges are set to the
+// value the reference's exchange gives them from the first iteration on: 0.0.
+__global__ void k_init(double* __restrict__ f0, double* __restrict__ f1, Layout L,
+                       const unsigned char* __restrict__ mask, BcArgs b, int west_zero, int east_zero,
+                       int shear_wave, double u0) {
+    const int y = (int)(blockIdx.x * blockDim.x + threadIdx.x) - 1;  // -1 .. ny
+    if (y > L.ny) return;
+    const bool ghost_row = (y < 0 || y >= L.ny);
+    for (int gx = blockIdx.y; gx < L.lnx + 2; gx += gridDim.y) {
+    const bool interior = !ghost_row && gx >= 1 && gx <= L.lnx;
+    double v[Q];
+    if (interior && mask[L.at(gx, y)]) {
+#pragma unroll
+        for (int i = 0; i < Q; ++i) v[i] = b.w[i];
+    } else if (!ghost_row && ((gx == 0 && west_zero) || (gx == L.lnx + 1 && east_zero))) {
+#pragma unroll
+        for (int i = 0; i < Q; ++i) v[i] = 0.0;
+    } else if (shear_wave) {
+        int yy = y < 0 ? y + L.ny : (y >= L.ny ? y - L.ny : y);
+        const double ux = u0 * sin(2.0 * 3.14159265358979323846 * (double)yy / (double)L.ny);
+        equilibrium_init(1.0, ux, 0.0, v);
+    } else {
+#pragma unroll
+        for (int i = 0; i < Q; ++i) v[i] = b.e[i];
+    }
+    store_cell(f0, L, gx, y, v);
+    store_cell(f1, L, gx, y, v);
+    }
+}
+
+__global__ void k_reset_ghosts(double* __restrict__ f, Layout L, BcArgs b, int west_zero, int east_zero) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    double z[Q] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (t < L.ny) {
+        store_cell(f, L, 0, t, west_zero ? z : b.e);
+        store_cell(f, L, L.lnx + 1, t, east_zero ? z : b.e);
+    }
+    if (t < L.lnx + 2) {
+        store_cell(f, L, t, -1, b.e);
+        store_cell(f, L, t, L.ny, b.e);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Observables.  f_current of the reference after its last iteration, for one interior cell,
+// given the newest post-collision buffer: pull, then boundary rules (fluid) or reversal (solid)
+// (include/LBMSolver.h:128-145, 147-265).
+__device__ __forceinline__ void current_from_next(const double* __restrict__ fnext, const Layout& L,
+                                                  const unsigned char* __restrict__ mask, const BcArgs& b, int x,
+                                                  int y, double f[Q], double& rho_bc, double& u_out) {
+    load_cell<true>(fnext, L, x + 1, y, f);
+    if (mask[L.at(x + 1, y)])
+        reverse(f);
+    else
+        apply_bc(f, x, y, L, b, rho_bc, u_out);
+}
+
+// rho, ux, uy as the reference's arrays hold them (see ObserveArgs in the header).
+__device__ __forceinline__ void macros_cell(const ObserveArgs& o, int x, int y, double& rho, double& ux,
+                                            double& uy) {
+    const Layout& L = o.L;
+    const bool solid = o.mask[L.at(x + 1, y)] != 0;
+    if (o.fresh) {  // include/LBMGrid.h:216-228
+        rho = 1.0;
+        uy = 0.0;
+        if (solid)
+            ux = 0.0;
+        else if (o.shear_wave)
+            ux = o.u0 * sin(2.0 * 3.14159265358979323846 * (double)y / (double)L.ny);
+        else
+            ux = o.bc.u_in;
+        return;
+    }
+    if (solid) {  // rho stays 1.0 from the constructor; include/LBMSolver.h:260-261
+        rho = 1.0;
+        ux = 0.0;
+        uy = 0.0;
+        return;
+    }
+    double f[Q], rb = 0.0, uo = 0.0;
+    if (!o.cur_is_next) {
+        // no iteration since an upload: moments of the uploaded f_current
+        load_cell<false>(o.cur, L, x + 1, y, f);
+        const Moments m = moments(f);
+        rho = m.rho; ux = m.ux; uy = m.uy;
+        return;
+    }
+    // moments stored by the last collision (include/LBMSolver.h:112-114): those of the f_current
+    // that collision read, i.e. of the PREVIOUS buffer's streamed + boundary-treated state
+    if (o.prev_is_next)
+        current_from_next(o.prev, L, o.mask, o.bc, x, y, f, rb, uo);
+    else
+        load_cell<false>(o.prev, L, x + 1, y, f);
+    const Moments m = moments(f);
+    rho = m.rho; ux = m.ux; uy = m.uy;
+    // ... then overwritten on the inlet / outlet columns by the boundary pass that built the
+    // newest f_current (include/LBMSolver.h:203-205, 232-234)
+    const bool on_in = o.bc.inlet && x == 0, on_out = o.bc.outlet && x == L.lnx - 1;
+    if (on_in || on_out) {
+        current_from_next(o.cur, L, o.mask, o.bc, x, y, f, rb, uo);
+        if (on_in) { rho = rb; ux = o.bc.u_in; uy = 0.0; }
+        if (on_out) { rho = 1.0; ux = uo; uy = 0.0; }
+    }
+}
+
+// 32 x 32 tile transpose: reads follow the SoA (y fastest), writes follow the reference's
+// interior row-major order (x fastest).
+__global__ void __launch_bounds__(256) k_macros(ObserveArgs o, double* __restrict__ rho, double* __restrict__ ux,
+                                                double* __restrict__ uy) {
+    __shared__ double t[3][32][33];
+    const Layout& L = o.L;
+    const int x0 = blockIdx.y * 32, y0 = blockIdx.x * 32;
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        const int x = x0 + k, y = y0 + threadIdx.x;
+        if (x < L.lnx && y < L.ny) {
+            double r, u, v;
+            macros_cell(o, x, y, r, u, v);
+            t[0][k][threadIdx.x] = r;
+            t[1][k][threadIdx.x] = u;
+            t[2][k][threadIdx.x] = v;
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        const int x = x0 + threadIdx.x, y = y0 + k;
+        if (x < L.lnx && y < L.ny) {
+            const long long g = (long long)y * L.lnx + x;
+            rho[g] = t[0][threadIdx.x][k];
+            ux[g] = t[1][threadIdx.x][k];
+            uy[g] = t[2][threadIdx.x][k];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_maxvel(const double* __restrict__ ux, const double* __restrict__ uy,
+                                                long long n, unsigned long long* out_bits) {
+    double m = 0.0;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const double v = ux[k] * ux[k] + uy[k] * uy[k];
+        m = v > m ? v : m;  // include/LBMGrid.h:330-331 (max of non-negative values; NaN never wins, as _mm256_max_pd)
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        const double other = __shfl_down_sync(0xffffffffu, m, s);
+        m = other > m ? other : m;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, (unsigned long long)__double_as_longlong(m));
+}
+
+// Export in the reference's padded AoS order, tile = 16 columns x 32 rows x 9 populations.
+constexpr int EX_TX = 16, EX_TY = 32;
+
+__global__ void __launch_bounds__(256) k_export_f(ObserveArgs o, int which, double* __restrict__ aos) {
+    __shared__ double t[Q][EX_TX][EX_TY + 1];
+    const Layout& L = o.L;
+    const int tnx = L.lnx + 2, tny = L.ny + 2;
+    const int gx0 = blockIdx.y * EX_TX, gy0 = blockIdx.x * EX_TY;  // padded coordinates
+    for (int c = threadIdx.x; c < EX_TX * EX_TY; c += blockDim.x) {
+        const int xl = c / EX_TY, yl = c % EX_TY;
+        const int gx = gx0 + xl, gy = gy0 + yl;
+        if (gx >= tnx || gy >= tny) continue;
+        const int x = gx - 1, y = gy - 1;
+        const bool ghost = (x < 0 || x >= L.lnx || y < 0 || y >= L.ny);
+        double f[Q];
+        // f_next before the first iteration equals f_current (include/LBMGrid.h:209-211)
+        const bool want_current = (which == 0) || !o.cur_is_next;
+        if (want_current) {
+            if (ghost) {  // never written after initialise
+#pragma unroll
+                for (int i = 0; i < Q; ++i) f[i] = o.bc.e[i];
+            } else if (o.cur_is_next) {
+                double rb, uo;
+                current_from_next(o.cur, L, o.mask, o.bc, x, y, f, rb, uo);
+            } else {
+                load_cell<false>(o.cur, L, gx, y, f);
+            }
+        } else {
+            load_cell<false>(o.cur, L, gx, y, f);
+        }
+#pragma unroll
+        for (int i = 0; i < Q; ++i) t[i][xl][yl] = f[i];
+    }
+    __syncthreads();
+    const int nxl = min(EX_TX, tnx - gx0);
+    for (int k = threadIdx.x; k < EX_TY * nxl * Q; k += blockDim.x) {
+        const int yl = k / (nxl * Q), e = k % (nxl * Q);
+        const int gy = gy0 + yl;
+        if (gy >= tny) break;
+        aos[((long long)gy * tnx + gx0) * Q + e] = t[e % Q][e / Q][yl];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_import_f(const double* __restrict__ aos, double* __restrict__ f, Layout L) {
+    __shared__ double t[Q][EX_TX][EX_TY + 1];
+    const int tnx = L.lnx + 2;
+    const int x0 = blockIdx.y * EX_TX, y0 = blockIdx.x * EX_TY;  // interior coordinates
+    const int nxl = min(EX_TX, L.lnx - x0);
+    for (int k = threadIdx.x; k < EX_TY * nxl * Q; k += blockDim.x) {
+        const int yl = k / (nxl * Q), e = k % (nxl * Q);
+        const int y = y0 + yl;
+        if (y >= L.ny) break;
+        t[e % Q][e / Q][yl] = aos[((long long)(y + 1) * tnx + (x0 + 1)) * Q + e];
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < Q * EX_TX * EX_TY; k += blockDim.x) {
+        const int i = k / (EX_TX * EX_TY), xl = (k / EX_TY) % EX_TX, yl = k % EX_TY;
+        const int x = x0 + xl, y = y0 + yl;
+        if (x < L.lnx && y < L.ny) f[i * L.plane + L.at(x + 1, y)] = t[i][xl][yl];
+    }
+}
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+cudaError_t launch_bulk_tma(bool pull, const StepArgs& a, cudaStream_t s, int x_begin, int x_end);  // lbm_bulk_tma.cu
+
+cudaError_t launch_bulk(int variant, bool pull, const StepArgs& a, cudaStream_t s, int x_begin, int x_end) {
+    if (x_end < 0) x_end = a.L.lnx;
+    const int ncols = x_end - x_begin;
+    if (ncols <= 0) return cudaSuccess;
+    if (variant == BULK_TMA && pull && !a.forced && a.write) {
+        cudaError_t e = launch_bulk_tma(pull, a, s, x_begin, x_end);
+        if (e != cudaErrorNotSupported) return e;  // shape not handled by the TMA kernel: fall through
+    }
+    if (variant != BULK_SCALAR && (a.L.ny % 2 == 0)) {
+        dim3 grid(cdiv(a.L.ny / 2, 128), ncols < 65535 ? ncols : 65535);
+        if (pull) {
+            if (a.forced) k_bulk_vec2<true, true><<<grid, 128, 0, s>>>(a, x_begin, x_end);
+            else k_bulk_vec2<true, false><<<grid, 128, 0, s>>>(a, x_begin, x_end);
+        } else {
+            if (a.forced) k_bulk_vec2<false, true><<<grid, 128, 0, s>>>(a, x_begin, x_end);
+            else k_bulk_vec2<false, false><<<grid, 128, 0, s>>>(a, x_begin, x_end);
+        }
+    } else {
+        dim3 grid(cdiv(a.L.ny, 256), ncols < 65535 ? ncols : 65535);
+        if (pull) {
+            if (a.forced) k_bulk_scalar<true, true><<<grid, 256, 0, s>>>(a, x_begin, x_end);
+            else k_bulk_scalar<true, false><<<grid, 256, 0, s>>>(a, x_begin, x_end);
+        } else {
+            if (a.forced) k_bulk_scalar<false, true><<<grid, 256, 0, s>>>(a, x_begin, x_end);
+            else k_bulk_scalar<false, false><<<grid, 256, 0, s>>>(a, x_begin, x_end);
+        }
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fixup(bool pull, const StepArgs& a, const BcArgs& b, const int2* ring, int n_ring,
+                         const int2* solids, int n_solid, cudaStream_t s) {
+    if (!pull) n_ring = 0;  // the first iteration collides f_current as it is: no boundary pass before it
+    const long long n = (long long)n_ring + n_solid;
+    if (n == 0) return cudaSuccess;
+    k_fixup<<<cdiv(n, 128), 128, 0, s>>>(a, b, pull ? 1 : 0, ring, n_ring, solids, n_solid);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_forces(const double* f_next, const Link* links, int n_links, double* out, cudaStream_t s) {
+    k_forces<<<1, 256, 0, s>>>(f_next, links, n_links, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_wrap(double* f, const Layout& L, int wrap_x, int wrap_y, cudaStream_t s) {
+    if (wrap_x) {
+        k_wrap<<<dim3(cdiv(L.ny, 256), Q), 256, 0, s>>>(f, L, 1, 0);
+    }
+    if (wrap_y) {
+        k_wrap<<<dim3(cdiv(L.lnx + 2, 256), Q), 256, 0, s>>>(f, L, 0, 1);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_init(double* f0, double* f1, const Layout& L, const unsigned char* mask, const BcArgs& b,
+                        int west_zero, int east_zero, int shear_wave, double u0, cudaStream_t s) {
+    dim3 grid(cdiv(L.ny + 2, 256), L.lnx + 2 < 65535 ? L.lnx + 2 : 65535);
+    k_init<<<grid, 256, 0, s>>>(f0, f1, L, mask, b, west_zero, east_zero, shear_wave, u0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_reset_ghosts(double* f, const Layout& L, const BcArgs& b, int west_zero, int east_zero,
+                                cudaStream_t s) {
+    const int n = (L.ny > L.lnx + 2) ? L.ny : L.lnx + 2;
+    k_reset_ghosts<<<cdiv(n, 256), 256, 0, s>>>(f, L, b, west_zero, east_zero);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_macros(const ObserveArgs& o, double* rho, double* ux, double* uy, cudaStream_t s) {
+    dim3 grid(cdiv(o.L.ny, 32), cdiv(o.L.lnx, 32));
+    k_macros<<<grid, dim3(32, 8), 0, s>>>(o, rho, ux, uy);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_maxvel(const double* ux, const double* uy, long long n, unsigned long long* out_bits,
+                          cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(out_bits, 0, sizeof(unsigned long long), s);
+    if (e != cudaSuccess) return e;
+    int blocks = cdiv(n, 256 * 8);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    k_maxvel<<<blocks, 256, 0, s>>>(ux, uy, n, out_bits);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_export_f(const ObserveArgs& o, int which, double* aos, cudaStream_t s) {
+    dim3 grid(cdiv(o.L.ny + 2, EX_TY), cdiv(o.L.lnx + 2, EX_TX));
+    k_export_f<<<grid, 256, 0, s>>>(o, which, aos);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_import_f(const double* aos, double* f, const Layout& L, cudaStream_t s) {
+    dim3 grid(cdiv(L.ny, EX_TY), cdiv(L.lnx, EX_TX));
+    k_import_f<<<grid, 256, 0, s>>>(aos, f, L);
+    return cudaGetLastError();
+}
+
+}  // namespace lbm

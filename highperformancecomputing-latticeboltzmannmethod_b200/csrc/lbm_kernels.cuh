@@ -1,0 +1,81 @@
+// lbm_kernels.cuh -- launch interface of the sm_100a kernels (definitions in lbm_kernels.cu and
+// lbm_bulk_tma.cu).  Host code (lbm_engine.cu) sees only these plain functions.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "lbm_layout.h"
+
+namespace lbm {
+
+// What the fix-up / observe kernels need to know about the boundaries of this slab.
+struct BcArgs {
+    double u_in;
+    int inlet;   // Zou-He velocity inlet on interior column 0   (slab touches x = 0, not periodic)
+    int outlet;  // Zou-He pressure outlet on column lnx-1        (slab touches x = gnx-1)
+    int walls;   // wall reflection on rows 0 and ny-1            (not periodic in y)
+    double w[9];  // populations a solid cell keeps for ever: eq(1,0,0)   
+    double e[9];  // initial equilibrium eq(1,u_in,0): value of every f_current ghost cell (F4)
+};
+
+struct StepArgs {
+    const double* src;  // post-collision populations of the previous iteration (or f_current when !pull)
+    double* dst;        // post-collision populations of this iteration
+    Layout L;
+    double tau_inv;
+    double Fx, Fy;   // body force (extension); 0 in the reference's channel
+    int forced;      // use bgk_forced
+    int* first_bad;  // device int, atomicMin'ed with bad_iter when an unstable value is seen
+    int bad_iter;    // reference timestep whose check_stability these pulled values belong to
+    int write;       // 0: check only, store nothing
+};
+
+enum BulkVariant { BULK_SCALAR = 0, BULK_VEC2 = 1, BULK_TMA = 2 };
+
+// Fused pull + collide over every interior cell, no boundary logic (reference
+// include/LBMSolver.h:84-145 minus the solid `continue`).  pull=false is the very first
+// iteration, which collides the initial f_current in place of a pulled state.
+cudaError_t launch_bulk(int variant, bool pull, const StepArgs& a, cudaStream_t s, int x_begin = 0, int x_end = -1);
+
+// Boundary + solid fix-up (reference include/LBMSolver.h:147-265 folded into the pull): ring
+// cells are re-pulled from src, get wall / Zou-He treatment in the reference's serial order, are
+// checked for stability, collided and stored; solid cells are reset to w.
+cudaError_t launch_fixup(bool pull, const StepArgs& a, const BcArgs& b, const int2* ring, int n_ring,
+                         const int2* solids, int n_solid, cudaStream_t s);
+
+// Momentum-exchange reduction (reference include/LBMIO.h:114-162) over a precomputed link list.
+cudaError_t launch_forces(const double* f_next, const Link* links, int n_links, double* out_fx_fy, cudaStream_t s);
+
+// Ghost wrap for the periodic extensions.
+cudaError_t launch_wrap(double* f, const Layout& L, int wrap_x, int wrap_y, cudaStream_t s);
+
+// Initial state (reference include/LBMGrid.h:185-246) into both buffers.
+cudaError_t launch_init(double* f0, double* f1, const Layout& L, const unsigned char* mask, const BcArgs& b,
+                        int west_zero, int east_zero, int shear_wave, double u0, cudaStream_t s);
+
+struct ObserveArgs {
+    const double* cur;   // newest buffer
+    const double* prev;  // the other buffer
+    Layout L;
+    const unsigned char* mask;  // padded, Layout indexing
+    BcArgs bc;
+    int cur_is_next;   // cur holds post-collision f_next (>= 1 iteration done) vs. an f_current
+    int prev_is_next;  // same for prev
+    int fresh;         // straight after initialise(): macroscopic fields are the exact constants
+    int shear_wave;
+    double u0;
+};
+// rho / ux / uy exactly as the reference's arrays hold them after the last iteration
+// (include/LBMSolver.h:112-114 with the overrides of :203-205, :232-234, :260-261).
+// Output interior row-major [y*lnx + x].
+cudaError_t launch_macros(const ObserveArgs& o, double* rho, double* ux, double* uy, cudaStream_t s);
+// max(ux^2+uy^2) -> *out_bits (as an order-preserving uint64 of a non-negative double).
+cudaError_t launch_maxvel(const double* ux, const double* uy, long long n, unsigned long long* out_bits,
+                          cudaStream_t s);
+// f_current / f_next in the reference's padded AoS order.
+cudaError_t launch_export_f(const ObserveArgs& o, int which, double* aos, cudaStream_t s);
+cudaError_t launch_import_f(const double* aos, double* f, const Layout& L, cudaStream_t s);
+// Ghost ring of one buffer back to the convention (W/E domain-edge columns 0, everything else e).
+cudaError_t launch_reset_ghosts(double* f, const Layout& L, const BcArgs& b, int west_zero, int east_zero,
+                                cudaStream_t s);
+
+}  // namespace lbm

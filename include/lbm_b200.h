@@ -1,0 +1,156 @@
+/*
+ * lbm_b200.h -- C ABI of liblbm_b200.so, the B200 (sm_100a) D2Q9 BGK collide-stream engine.
+ *
+ * This is the drop-in boundary for the per-timestep path of
+ * LGMOak/HighPerformanceComputing-LatticeBoltzmannMethod.  The reference has no FFI layer; its
+ * boundary is the header-level C++ API that src/main.cpp:11-21 and Solver::run consume.  The
+ * C++ headers in this directory (LBMConfig.h, LBMGrid.h, LBMSolver.h, LBMIO.h) keep that API and
+ * forward to the entry points below; tests and bench.py bind the same entry points with ctypes.
+ * Each entry point names the reference interface it replaces (paths relative to the reference
+ * repository root).
+ *
+ * Conventions: plain C types only; every function returns 0 on success or a negative
+ * lbm_status; lbm_last_error() gives the message.  One host thread per handle.  All device
+ * work runs on streams owned by the handle.  There is no CPU fallback: without a CUDA device
+ * lbm_create* fails with LBM_ERR_CUDA.
+ *
+ * Host array layouts are the reference's (include/LBMGrid.h:105-111):
+ *   populations  padded AoS   [(gy*(lnx+2) + gx)*9 + i], gx in [0,lnx+2), gy in [0,ny+2)
+ *   rho/ux/uy    interior     [y*lnx + x]
+ *   solid mask   interior     [y*lnx + x], one byte per cell
+ * where lnx is the width of this handle's x-slab (== nx for a single-GPU handle).
+ */
+#ifndef LBM_B200_H
+#define LBM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBM_B200_ABI_VERSION 1
+
+typedef enum lbm_status {
+    LBM_OK = 0,
+    LBM_ERR_INVALID = -1,  /* bad argument / bad state */
+    LBM_ERR_CUDA = -2,     /* CUDA runtime or driver error (incl. "no device") */
+    LBM_ERR_NCCL = -3,
+    LBM_ERR_NOMEM = -4,
+    LBM_ERR_UNSTABLE = -5, /* only from calls documented to return it */
+    LBM_ERR_IO = -6
+} lbm_status;
+
+/* Extensions beyond the reference (the reference has no periodic and no
+ * body-force mode on this branch).  flags == 0 is exactly the reference's channel. */
+enum {
+    LBM_FLAG_PERIODIC_X = 1,  /* wrap in x instead of Zou-He inlet/outlet            */
+    LBM_FLAG_PERIODIC_Y = 2,  /* wrap in y instead of the wall reflection             */
+    LBM_FLAG_NO_CYLINDER = 4, /* obstacle-free domain                                 */
+    LBM_FLAG_SHEAR_WAVE_INIT = 8 /* u = (inlet_velocity*sin(2*pi*y/ny), 0) initial field */
+};
+
+/* Mirrors LBM::SimulationParams (include/LBMConfig.h:36-52) field for field, then extensions. */
+typedef struct lbm_params {
+    double tau;
+    double inlet_velocity;
+    int32_t nx, ny;
+    int32_t num_timesteps;
+    int32_t output_frequency;
+    double cylinder_x, cylinder_y, cylinder_radius; /* fractions of nx, ny, ny */
+    int32_t vtk_start_step;
+    int32_t flags;       /* LBM_FLAG_* */
+    double body_force_x; /* f_eq + 3 w_i c_i.F form of include/LBMUtils.h:98,117 */
+    double body_force_y;
+} lbm_params;
+
+typedef struct lbm_info {
+    int32_t abi_version;
+    int32_t global_nx, global_ny;
+    int32_t local_nx, local_ny;
+    int32_t x_start, y_start;
+    int32_t rank, world;
+    int32_t device;
+    int32_t cyl_x, cyl_y, cyl_r; /* integer cells, LBMConfig.h:61-65 */
+    int32_t solid_cells;         /* in this slab */
+    int32_t links;               /* momentum-exchange links owned by this slab */
+    int32_t iteration;           /* reference iterations completed so far */
+    int64_t bytes_per_buffer;    /* one SoA population buffer on the device */
+    int32_t row_pitch;           /* doubles between consecutive x columns in a plane */
+    int32_t kernel_variant;
+} lbm_info;
+
+typedef struct lbm_solver* lbm_handle;
+
+/* ---- lifecycle: Solver::Solver + Grid::Grid (include/LBMSolver.h:23, include/LBMGrid.h:57-103) ---- */
+int lbm_create(const lbm_params* p, int device, lbm_handle* out);
+/* One x-slab of a multi-GPU job, one process per GPU.  Replaces MPI_Cart_create and the
+ * neighbour discovery of include/LBMGrid.h:347-364 with contiguous x-slabs (py == 1).
+ * nccl_unique_id: the 128 bytes from lbm_nccl_unique_id() on rank 0, broadcast by the caller. */
+int lbm_create_slab(const lbm_params* p, int device, int rank, int world, const void* nccl_unique_id,
+                    lbm_handle* out);
+int lbm_nccl_unique_id(void* out128);
+int lbm_destroy(lbm_handle h);
+const char* lbm_last_error(lbm_handle h); /* h may be NULL: error of the last failed create */
+int lbm_get_info(lbm_handle h, lbm_info* out);
+
+/* ---- set-up: Solver::initialise (include/LBMSolver.h:31-41) ---- */
+int lbm_setup_geometry(lbm_handle h, int* solid_count); /* Grid::setup_geometry, LBMGrid.h:152-183 */
+int lbm_initialise(lbm_handle h, double inlet_u);       /* Grid::initialise,     LBMGrid.h:185-246 */
+
+/* ---- the hot path: the loop body of Solver::run (include/LBMSolver.h:48-76) ---- */
+/* Advance n reference iterations asynchronously: fused pull+boundary+collide kernels, the halo
+ * exchange (Grid::exchange_ghost_cells, LBMGrid.h:249-283) and, on iterations t with
+ * t % output_frequency == 0, the momentum-exchange reduction (IOManager::record_forces,
+ * LBMIO.h:114-168).  Stability flags accumulate on the device (Grid::check_stability,
+ * LBMGrid.h:285-317). */
+int lbm_step(lbm_handle h, int n_steps);
+/* Solver::run for n more iterations with the reference's observable behaviour: forces rows
+ * {t, Fx, Fy, C_D, C_L} for every output step (LBMIO.h:171-185), up to max_rows; stops at the
+ * first unstable iteration and reports it in *unstable_at (else -1), exactly the t of
+ * "Simulation unstable at timestep t" (LBMSolver.h:60-64).  Returns LBM_OK also when unstable. */
+int lbm_run(lbm_handle h, int n_steps, double* forces_rows, int max_rows, int* n_rows, int* unstable_at);
+int lbm_sync(lbm_handle h);
+
+/* IOManager::record_forces (LBMIO.h:114-168) for the current f_next: slab-local partial sums. */
+int lbm_get_forces(lbm_handle h, double* fx, double* fy);
+/* Grid::check_stability (LBMGrid.h:285-317) of the current f_current, plus everything flagged
+ * since the last initialise/upload.  *first_bad_step is the reference timestep or -1. */
+int lbm_check_stability(lbm_handle h, int* ok, int* first_bad_step);
+/* Grid::max_velocity (LBMGrid.h:319-344): slab-local sqrt(max(ux^2+uy^2)). */
+int lbm_max_velocity(lbm_handle h, double* out);
+
+/* ---- observable state: Grid accessors (include/LBMGrid.h:115-129,145) ---- */
+enum { LBM_F_CURRENT = 0, LBM_F_NEXT = 1 };
+int lbm_download_f(lbm_handle h, int which, double* aos_padded);
+int lbm_download_macros(lbm_handle h, double* rho, double* ux, double* uy);
+int lbm_download_solid(lbm_handle h, unsigned char* mask);
+/* Replace the state by a given f_current (padded AoS; ghost entries ignored).  Used for
+ * restart and for parity tests on seeded random states.  `iteration` is the reference timestep
+ * the next lbm_step will execute. */
+int lbm_upload_f(lbm_handle h, const double* f_current_aos_padded, int iteration);
+
+/* ---- async output: replaces the MPI gathers of Solver::write_vtk_frame (LBMSolver.h:269-362)
+ * and IOManager::gather_and_reconstruct_field (LBMIO.h:225-300).  Snapshots rho/ux/uy of the
+ * current state into caller-owned host buffers (pinned via lbm_host_alloc for true overlap) on
+ * a copy stream; the compute stream only waits for the on-device macro kernel. */
+int lbm_snapshot_begin(lbm_handle h, double* rho, double* ux, double* uy);
+int lbm_snapshot_wait(lbm_handle h);
+int lbm_host_alloc(void** ptr, size_t bytes); /* cudaHostAlloc */
+int lbm_host_free(void* ptr);
+
+/* ---- measurement ---- */
+/* Run n_steps and time them with CUDA events on the compute stream.  ms_total covers the whole
+ * region; ms_bulk is the summed duration of the bulk collide-stream kernel launches only
+ * (events around each launch; use a small n_steps for that, it serialises the stream). */
+int lbm_time_steps(lbm_handle h, int n_steps, int per_kernel, float* ms_total, float* ms_bulk, int* launches);
+/* Kernel variant of the bulk kernel: 0 = scalar reference kernel, 1 = vectorised LDG/STG,
+ * 2 = TMA-pipelined persistent kernel.  Default: best measured. */
+int lbm_set_kernel_variant(lbm_handle h, int variant);
+int lbm_device_count(int* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBM_B200_H */
