@@ -102,7 +102,7 @@ EXPORTS = [
     "lbm_setup_geometry", "lbm_initialise", "lbm_step", "lbm_run", "lbm_sync", "lbm_get_forces",
     "lbm_check_stability", "lbm_max_velocity", "lbm_download_f", "lbm_download_macros", "lbm_download_solid",
     "lbm_upload_f", "lbm_snapshot_begin", "lbm_snapshot_wait", "lbm_host_alloc", "lbm_host_free", "lbm_time_steps",
-    "lbm_set_kernel_variant", "lbm_device_count",
+    "lbm_set_kernel_variant", "lbm_device_count", "lbm_get_counters", "lbm_event_record", "lbm_event_elapsed",
 ]
 
 _lib = None
@@ -143,6 +143,10 @@ def load():
     L.lbm_time_steps.argtypes = [H, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), I]
     L.lbm_set_kernel_variant.argtypes = [H, C.c_int]
     L.lbm_device_count.argtypes = [I]
+    LL = C.POINTER(C.c_longlong)
+    L.lbm_get_counters.argtypes = [H, LL, LL, LL]
+    L.lbm_event_record.argtypes = [H, C.c_int]
+    L.lbm_event_elapsed.argtypes = [H, C.c_int, C.c_int, C.POINTER(C.c_float)]
     for name in EXPORTS:
         if name != "lbm_last_error":
             getattr(L, name).restype = C.c_int
@@ -261,9 +265,11 @@ class Solver:
         return v.value
 
     # -- Grid accessors (LBMGrid.h:115-129,145) ---------------------------------------------
-    def f(self, which: int) -> np.ndarray:
+    def f(self, which: int, out: np.ndarray | None = None) -> np.ndarray:
         i = self.info()
-        out = np.empty((i.local_ny + 2, i.local_nx + 2, 9))
+        if out is None:
+            out = np.empty((i.local_ny + 2, i.local_nx + 2, 9))
+        assert out.shape == (i.local_ny + 2, i.local_nx + 2, 9) and out.flags.c_contiguous and out.dtype == np.float64
         self._ck(load().lbm_download_f(self._h, which, out.ctypes.data))
         return out
 
@@ -273,9 +279,11 @@ class Solver:
     def f_next(self):
         return self.f(F_NEXT)
 
-    def macros(self):
+    def macros(self, out=None):
         i = self.info()
-        rho, ux, uy = (np.empty((i.local_ny, i.local_nx)) for _ in range(3))
+        rho, ux, uy = out if out is not None else (np.empty((i.local_ny, i.local_nx)) for _ in range(3))
+        for a in (rho, ux, uy):
+            assert a.shape == (i.local_ny, i.local_nx) and a.flags.c_contiguous and a.dtype == np.float64
         self._ck(load().lbm_download_macros(self._h, rho.ctypes.data, ux.ctypes.data, uy.ctypes.data))
         return rho, ux, uy
 
@@ -303,6 +311,21 @@ class Solver:
         a, b, l = C.c_float(), C.c_float(), C.c_int()
         self._ck(load().lbm_time_steps(self._h, n, int(per_kernel), C.byref(a), C.byref(b), C.byref(l)))
         return a.value, b.value, l.value
+
+    def counters(self):
+        """(launches since creation, bulk launches, bulk cells) -- the last two for the last
+        time_steps(per_kernel=True)."""
+        a, b, c = C.c_longlong(), C.c_longlong(), C.c_longlong()
+        self._ck(load().lbm_get_counters(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def event_record(self, slot: int):
+        self._ck(load().lbm_event_record(self._h, slot))
+
+    def event_elapsed(self, a: int, b: int) -> float:
+        ms = C.c_float()
+        self._ck(load().lbm_event_elapsed(self._h, a, b, C.byref(ms)))
+        return ms.value
 
     def set_kernel_variant(self, v: int):
         self._ck(load().lbm_set_kernel_variant(self._h, v))

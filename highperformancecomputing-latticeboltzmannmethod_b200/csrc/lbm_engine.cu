@@ -82,6 +82,8 @@ struct lbm_solver {
     long long launches = 0;
     std::vector<cudaEvent_t> bulk_events;  // pairs, only while per-kernel timing is on
     bool time_bulk = false;
+    long long bulk_timed_launches = 0, bulk_timed_cells = 0;  // of the last lbm_time_steps(per_kernel)
+    cudaEvent_t marks[LBM_EVENT_SLOTS] = {};                  // lbm_event_record / lbm_event_elapsed
 
     std::string err;
 };
@@ -283,6 +285,8 @@ int step_one(lbm_handle h) {
             cudaEventRecord(e1, h->stream);
             h->bulk_events.push_back(e0);
             h->bulk_events.push_back(e1);
+            h->bulk_timed_launches += 1;
+            h->bulk_timed_cells += (long long)(x1 - x0) * L.ny;
             return r;
         }
         return launch_bulk(h->variant, pull, a, h->stream, x0, x1);
@@ -532,6 +536,8 @@ int lbm_destroy(lbm_handle h) {
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     if (h->comm) nccl_api().CommDestroy(h->comm);
     for (cudaEvent_t e : h->bulk_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->marks)
+        if (e) cudaEventDestroy(e);
     cudaFree(h->f[0]); cudaFree(h->f[1]); cudaFree(h->d_mask); cudaFree(h->d_ring); cudaFree(h->d_solids);
     cudaFree(h->d_links); cudaFree(h->d_rho); cudaFree(h->d_ux); cudaFree(h->d_uy); cudaFree(h->d_scratch);
     cudaFree(h->d_first_bad); cudaFree(h->d_forces); cudaFree(h->d_maxbits);
@@ -826,6 +832,7 @@ int lbm_time_steps(lbm_handle h, int n_steps, int per_kernel, float* ms_total, f
     CU(h, cudaEventCreate(&e1));
     const long long l0 = h->launches;
     h->time_bulk = per_kernel != 0;
+    if (h->time_bulk) h->bulk_timed_launches = h->bulk_timed_cells = 0;
     CU(h, cudaStreamSynchronize(h->comm_stream));
     CU(h, cudaStreamSynchronize(h->stream));
     CU(h, cudaEventRecord(e0, h->stream));
@@ -851,6 +858,37 @@ int lbm_time_steps(lbm_handle h, int n_steps, int per_kernel, float* ms_total, f
     if (launches) *launches = (int)(h->launches - l0);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    return LBM_OK;
+}
+
+int lbm_get_counters(lbm_handle h, long long* launches, long long* bulk_launches, long long* bulk_cells) {
+    CHECK_H(h);
+    if (launches) *launches = h->launches;
+    if (bulk_launches) *bulk_launches = h->bulk_timed_launches;
+    if (bulk_cells) *bulk_cells = h->bulk_timed_cells;
+    return LBM_OK;
+}
+
+int lbm_event_record(lbm_handle h, int slot) {
+    CHECK_H(h);
+    if (slot < 0 || slot >= LBM_EVENT_SLOTS) return fail(h, LBM_ERR_INVALID, "event slot out of range");
+    CU(h, cudaSetDevice(h->device));
+    if (!h->marks[slot]) CU(h, cudaEventCreate(&h->marks[slot]));
+    // everything the handle has in flight on its side streams is ordered before the mark
+    if (h->west >= 0 || h->east >= 0) CU(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
+    if (h->snapshot_pending) CU(h, cudaStreamWaitEvent(h->stream, h->ev_snapshot, 0));
+    CU(h, cudaEventRecord(h->marks[slot], h->stream));
+    return LBM_OK;
+}
+
+int lbm_event_elapsed(lbm_handle h, int slot_a, int slot_b, float* ms) {
+    CHECK_H(h);
+    if (slot_a < 0 || slot_a >= LBM_EVENT_SLOTS || slot_b < 0 || slot_b >= LBM_EVENT_SLOTS || !ms ||
+        !h->marks[slot_a] || !h->marks[slot_b])
+        return fail(h, LBM_ERR_INVALID, "bad event slots");
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaEventSynchronize(h->marks[slot_b]));
+    CU(h, cudaEventElapsedTime(ms, h->marks[slot_a], h->marks[slot_b]));
     return LBM_OK;
 }
 

@@ -145,6 +145,15 @@ int lbm_host_free(void* ptr);
  * region; ms_bulk is the summed duration of the bulk collide-stream kernel launches only
  * (events around each launch; use a small n_steps for that, it serialises the stream). */
 int lbm_time_steps(lbm_handle h, int n_steps, int per_kernel, float* ms_total, float* ms_bulk, int* launches);
+/* Kernel launches issued by this handle since creation; launches and lattice cells of the bulk
+ * collide-stream kernel covered by ms_bulk of the last lbm_time_steps(per_kernel=1). */
+int lbm_get_counters(lbm_handle h, long long* launches, long long* bulk_launches, long long* bulk_cells);
+/* CUDA-event marks on the handle's compute stream (after everything its side streams have in
+ * flight), so that a caller can time any sequence of entry points -- uploads, runs, downloads --
+ * on the device rather than by wall clock. */
+#define LBM_EVENT_SLOTS 8
+int lbm_event_record(lbm_handle h, int slot);
+int lbm_event_elapsed(lbm_handle h, int slot_a, int slot_b, float* ms);
 /* Kernel variant of the bulk kernel: 0 = scalar reference kernel, 1 = vectorised LDG/STG,
  * 2 = TMA-pipelined persistent kernel.  Default: best measured. */
 int lbm_set_kernel_variant(lbm_handle h, int variant);

@@ -55,6 +55,12 @@ def random_state(case, seed, amplitude=0.05):
     rng = np.random.default_rng(seed)
     w = np.array([4 / 9] + [1 / 9] * 4 + [1 / 36] * 4)
     f = w * (1.0 + amplitude * rng.standard_normal((case.ny + 2, case.nx + 2, 9)))
+    # the ghost ring of f_current is never written after Grid::initialise (SURVEY.md Appendix A
+    # step 6): a reachable state always holds eq(1, u_in, 0) there, and lbm_upload_f ignores it
+    o = O.Oracle(case)  # keep alive: f_current is a view of its memory
+    init = o.f_current.copy()
+    for sl in ((0, slice(None)), (-1, slice(None)), (slice(None), 0), (slice(None), -1)):
+        f[sl] = init[sl]
     return np.ascontiguousarray(f)
 
 
