@@ -20,7 +20,7 @@ flag, and on every output_frequency-th step the momentum-exchange reduction.
             amount to.  Timed with CUDA events around the whole segment.
   roofline  bulk collide-stream kernel: 144 B per cell update (9 fp64 loads + 9 fp64 stores,
             SURVEY.md section 8d) x cells per launch / average launch duration (CUDA events
-            around every bulk launch INSIDE the timed region), against MEASURED_PEAKS.json.
+            around the bulk launch of every 8th step INSIDE the timed region), against MEASURED_PEAKS.json.
   cpu_baseline  oracle/_ref/lbm_ref_fast (the unmodified reference headers built with the
             reference's own flags, all host cores) on a bounded sample of the same workload.
 
@@ -338,7 +338,7 @@ def main():
     s.step(args.warmup)
     s.sync()
     barrier()
-    per_kernel = args.steps <= 20000
+    per_kernel = 8 if args.steps >= 64 else 1  # CUDA events around the bulk launch of every 8th step
     launches0 = s.counters()[0]
     w0 = time.time()
     ms_total, ms_bulk, launches = s.time_steps(args.steps, per_kernel)
@@ -360,7 +360,7 @@ def main():
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic_per_launch(args.workload), "kernel": "k_bulk (fused pull collide-stream)",
                 "bytes_per_launch": (bulk_cells / bulk_launches) * BYTES_PER_UPDATE, "avg_launch_ms": bulk_ms,
-                "launches_timed": bulk_launches, "kernel_share_of_step": ms_bulk / ms_total, "peak_source": peak_src,
+                "launches_timed": bulk_launches, "kernel_share_of_step": bulk_ms * args.steps / ms_total, "peak_source": peak_src,
                 "whole_step_frac": value * 1e6 * BYTES_PER_UPDATE / 1e9 / args.gpus / peak}
     else:
         roof = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None}

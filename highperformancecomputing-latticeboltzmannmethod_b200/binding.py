@@ -103,6 +103,7 @@ EXPORTS = [
     "lbm_check_stability", "lbm_max_velocity", "lbm_download_f", "lbm_download_macros", "lbm_download_solid",
     "lbm_upload_f", "lbm_snapshot_begin", "lbm_snapshot_wait", "lbm_host_alloc", "lbm_host_free", "lbm_time_steps",
     "lbm_set_kernel_variant", "lbm_device_count", "lbm_get_counters", "lbm_event_record", "lbm_event_elapsed",
+    "lbm_bootstrap_env", "lbm_set_params", "lbm_snapshot_begin_slot", "lbm_snapshot_wait_slot", "lbm_allreduce", "lbm_gather_macros",
 ]
 
 _lib = None
@@ -147,6 +148,12 @@ def load():
     L.lbm_get_counters.argtypes = [H, LL, LL, LL]
     L.lbm_event_record.argtypes = [H, C.c_int]
     L.lbm_event_elapsed.argtypes = [H, C.c_int, C.c_int, C.POINTER(C.c_float)]
+    L.lbm_snapshot_begin_slot.argtypes = [H, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.lbm_snapshot_wait_slot.argtypes = [H, C.c_int]
+    L.lbm_bootstrap_env.argtypes = [I, I, I, C.c_void_p]
+    L.lbm_set_params.argtypes = [H, C.POINTER(CParams)]
+    L.lbm_allreduce.argtypes = [H, D, C.c_int, C.c_int]
+    L.lbm_gather_macros.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p]
     for name in EXPORTS:
         if name != "lbm_last_error":
             getattr(L, name).restype = C.c_int
@@ -306,7 +313,28 @@ class Solver:
         self._ck(load().lbm_snapshot_wait(self._h))
 
     # -- measurement ------------------------------------------------------------------------
-    def time_steps(self, n: int, per_kernel: bool = False):
+    def allreduce(self, values, op: int = 0) -> np.ndarray:
+        """In-place NCCL all-reduce of a few host doubles over the slabs (0 sum, 1 min, 2 max)."""
+        a = np.ascontiguousarray(values, dtype=np.float64).copy()
+        self._ck(load().lbm_allreduce(self._h, a.ctypes.data_as(C.POINTER(C.c_double)), a.size, op))
+        return a
+
+    def gather_macros(self):
+        """rho, ux, uy of the whole channel on rank 0 ([global_ny, global_nx]); None elsewhere."""
+        i = self.info()
+        if i.rank == 0:
+            out = tuple(np.empty((i.global_ny, i.global_nx)) for _ in range(3))
+            self._ck(load().lbm_gather_macros(self._h, *(a.ctypes.data for a in out)))
+            return out
+        self._ck(load().lbm_gather_macros(self._h, None, None, None))
+        return None
+
+    def set_params(self, params: "SimulationParams"):
+        cp = params.to_c()
+        self._ck(load().lbm_set_params(self._h, C.byref(cp)))
+        self.params = params
+
+    def time_steps(self, n: int, per_kernel: int = 0):
         """(ms_total, ms_bulk_kernels, launches) for n iterations, CUDA events on the compute stream."""
         a, b, l = C.c_float(), C.c_float(), C.c_int()
         self._ck(load().lbm_time_steps(self._h, n, int(per_kernel), C.byref(a), C.byref(b), C.byref(l)))

@@ -17,7 +17,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <initializer_list>
 #include <string>
+#include <unistd.h>
 #include <vector>
 
 #include "../../include/lbm_b200.h"
@@ -30,6 +32,7 @@ using namespace lbm;
 
 namespace {
 thread_local std::string g_create_error;
+std::string g_id_file;  // rank 0: NCCL id file of lbm_bootstrap_env, removed after the communicator is up
 constexpr int FORCE_SLOTS = 1024;
 }  // namespace
 
@@ -43,6 +46,7 @@ struct lbm_solver {
     cudaStream_t stream = nullptr, copy_stream = nullptr, comm_stream = nullptr;
     cudaEvent_t ev_macros = nullptr, ev_snapshot = nullptr, ev_edge = nullptr, ev_comm = nullptr;
     bool snapshot_pending = false;
+    cudaEvent_t ev_slot[LBM_SNAPSHOT_SLOTS] = {};  // completion of the D2H copies of lbm_snapshot_begin_slot
 
     double* f[2] = {nullptr, nullptr};
     int cur = 0;
@@ -77,11 +81,14 @@ struct lbm_solver {
     bool overlap = true;
 
     ncclComm_t comm = nullptr;
+    double* d_red = nullptr;       // small device scratch for lbm_allreduce
+    double* d_gather = nullptr;    // rank 0: one slab of rho/ux/uy received from a peer
+    int* d_first_bad_all = nullptr;
     int west = -1, east = -1;  // neighbour ranks or -1
 
     long long launches = 0;
     std::vector<cudaEvent_t> bulk_events;  // pairs, only while per-kernel timing is on
-    bool time_bulk = false;
+    int time_bulk = 0;  // 0 = off, n = events around the bulk launch of every n-th iteration
     long long bulk_timed_launches = 0, bulk_timed_cells = 0;  // of the last lbm_time_steps(per_kernel)
     cudaEvent_t marks[LBM_EVENT_SLOTS] = {};                  // lbm_event_record / lbm_event_elapsed
 
@@ -276,7 +283,7 @@ int step_one(lbm_handle h) {
     const bool split = multi && h->overlap && L.lnx >= 4;
 
     auto bulk = [&](int x0, int x1) -> cudaError_t {
-        if (h->time_bulk) {
+        if (h->time_bulk && (h->iter % h->time_bulk) == 0) {
             cudaEvent_t e0, e1;
             cudaEventCreate(&e0);
             cudaEventCreate(&e1);
@@ -382,9 +389,16 @@ int check_pending(lbm_handle h) {
     return LBM_OK;
 }
 
+// The verdict of Grid::check_stability is global (MPI_Allreduce MIN, include/LBMGrid.h:315):
+// with several slabs every rank gets the smallest failing timestep of any of them.
 int read_first_bad(lbm_handle h, int* out) {
     int v = INT_MAX;
-    CU(h, cudaMemcpyAsync(&v, h->d_first_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    const int* src = h->d_first_bad;
+    if (h->comm) {
+        NC(h, nccl_api().AllReduce(h->d_first_bad, h->d_first_bad_all, 1, ncclInt, ncclMin, h->comm, h->stream));
+        src = h->d_first_bad_all;
+    }
+    CU(h, cudaMemcpyAsync(&v, src, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     *out = v;
     return LBM_OK;
@@ -466,6 +480,8 @@ int create_common(const lbm_params* p, int device, int rank, int world, const vo
     CUC(cudaMalloc(&h->d_first_bad, sizeof(int)));
     CUC(cudaMalloc(&h->d_forces, sizeof(double) * 2 * FORCE_SLOTS));
     CUC(cudaMalloc(&h->d_maxbits, sizeof(unsigned long long)));
+    CUC(cudaMalloc(&h->d_red, sizeof(double) * LBM_REDUCE_MAX));
+    CUC(cudaMalloc(&h->d_first_bad_all, sizeof(int)));
     const int big = INT_MAX;
     CUC(cudaMemcpyAsync(h->d_first_bad, &big, sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CUC(cudaStreamSynchronize(h->stream));
@@ -480,6 +496,10 @@ int create_common(const lbm_params* p, int device, int rank, int world, const vo
         std::memcpy(&id, uid, sizeof(id));
         ncclResult_t r = N.CommInitRank(&h->comm, world, id, rank);
         if (r != ncclSuccess) return bail(LBM_ERR_NCCL, std::string("ncclCommInitRank: ") + N.GetErrorString(r));
+        if (!g_id_file.empty()) {
+            std::remove(g_id_file.c_str());
+            g_id_file.clear();
+        }
     }
     // ring list etc. for an obstacle-free domain; lbm_setup_geometry adds the cylinder
     {
@@ -538,9 +558,12 @@ int lbm_destroy(lbm_handle h) {
     for (cudaEvent_t e : h->bulk_events) cudaEventDestroy(e);
     for (cudaEvent_t e : h->marks)
         if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_slot)
+        if (e) cudaEventDestroy(e);
     cudaFree(h->f[0]); cudaFree(h->f[1]); cudaFree(h->d_mask); cudaFree(h->d_ring); cudaFree(h->d_solids);
     cudaFree(h->d_links); cudaFree(h->d_rho); cudaFree(h->d_ux); cudaFree(h->d_uy); cudaFree(h->d_scratch);
     cudaFree(h->d_first_bad); cudaFree(h->d_forces); cudaFree(h->d_maxbits);
+    cudaFree(h->d_red); cudaFree(h->d_gather); cudaFree(h->d_first_bad_all);
     if (h->ev_macros) cudaEventDestroy(h->ev_macros);
     if (h->ev_snapshot) cudaEventDestroy(h->ev_snapshot);
     if (h->ev_edge) cudaEventDestroy(h->ev_edge);
@@ -800,6 +823,25 @@ int lbm_snapshot_begin(lbm_handle h, double* rho, double* ux, double* uy) {
     return LBM_OK;
 }
 
+int lbm_snapshot_begin_slot(lbm_handle h, int slot, double* rho, double* ux, double* uy) {
+    CHECK_H(h);
+    if (slot < 0 || slot >= LBM_SNAPSHOT_SLOTS) return fail(h, LBM_ERR_INVALID, "snapshot slot out of range");
+    CU(h, cudaSetDevice(h->device));
+    if (!h->ev_slot[slot]) CU(h, cudaEventCreateWithFlags(&h->ev_slot[slot], cudaEventDisableTiming));
+    int rc = lbm_snapshot_begin(h, rho, ux, uy);
+    if (rc) return rc;
+    CU(h, cudaEventRecord(h->ev_slot[slot], h->copy_stream));
+    return LBM_OK;
+}
+
+// Safe to call from a second host thread (an output writer): touches nothing but the event.
+int lbm_snapshot_wait_slot(lbm_handle h, int slot) {
+    CHECK_H(h);
+    if (slot < 0 || slot >= LBM_SNAPSHOT_SLOTS || !h->ev_slot[slot]) return LBM_ERR_INVALID;
+    cudaError_t e = cudaEventSynchronize(h->ev_slot[slot]);
+    return e == cudaSuccess ? LBM_OK : LBM_ERR_CUDA;
+}
+
 int lbm_snapshot_wait(lbm_handle h) {
     CHECK_H(h);
     CU(h, cudaSetDevice(h->device));
@@ -831,13 +873,13 @@ int lbm_time_steps(lbm_handle h, int n_steps, int per_kernel, float* ms_total, f
     CU(h, cudaEventCreate(&e0));
     CU(h, cudaEventCreate(&e1));
     const long long l0 = h->launches;
-    h->time_bulk = per_kernel != 0;
+    h->time_bulk = per_kernel > 0 ? per_kernel : 0;
     if (h->time_bulk) h->bulk_timed_launches = h->bulk_timed_cells = 0;
     CU(h, cudaStreamSynchronize(h->comm_stream));
     CU(h, cudaStreamSynchronize(h->stream));
     CU(h, cudaEventRecord(e0, h->stream));
     int rc = lbm_step(h, n_steps);
-    h->time_bulk = false;
+    h->time_bulk = 0;
     if (rc) return rc;
     if (h->west >= 0 || h->east >= 0) CU(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
     CU(h, cudaEventRecord(e1, h->stream));
@@ -889,6 +931,121 @@ int lbm_event_elapsed(lbm_handle h, int slot_a, int slot_b, float* ms) {
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaEventSynchronize(h->marks[slot_b]));
     CU(h, cudaEventElapsedTime(ms, h->marks[slot_a], h->marks[slot_b]));
+    return LBM_OK;
+}
+
+// ---- multi-slab plumbing -------------------------------------------------------------------
+namespace {
+const char* env_first(std::initializer_list<const char*> names) {
+    for (const char* n : names)
+        if (const char* v = std::getenv(n)) return v;
+    return nullptr;
+}
+}  // namespace
+
+int lbm_bootstrap_env(int* rank, int* world, int* local_rank, void* id128) {
+    // torchrun: RANK / WORLD_SIZE / LOCAL_RANK.  mpirun or srun used purely as a process launcher:
+    // the usual OMPI_ / PMI_ / SLURM_ variables.  No launcher: one slab.
+    const char* r = env_first({"LBM_B200_RANK", "RANK", "OMPI_COMM_WORLD_RANK", "PMI_RANK", "SLURM_PROCID"});
+    const char* w = env_first({"LBM_B200_WORLD", "WORLD_SIZE", "OMPI_COMM_WORLD_SIZE", "PMI_SIZE", "SLURM_NTASKS"});
+    const char* l = env_first({"LBM_B200_LOCAL_RANK", "LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "MPI_LOCALRANKID", "SLURM_LOCALID"});
+    const int wr = w ? std::atoi(w) : 1;
+    const int rr = (r && wr > 1) ? std::atoi(r) : 0;
+    if (wr < 1 || rr < 0 || rr >= wr) return fail(nullptr, LBM_ERR_INVALID, "inconsistent RANK / WORLD_SIZE in the environment");
+    if (rank) *rank = rr;
+    if (world) *world = wr;
+    if (local_rank) *local_rank = (l && wr > 1) ? std::atoi(l) : rr;
+    if (wr == 1 || !id128) return LBM_OK;
+    // The 128-byte NCCL id travels through a file that only ranks of this launch agree on: all
+    // ranks are children of one launcher process, so its pid names the file.
+    char path[512];
+    if (const char* f = std::getenv("LBM_B200_ID_FILE"))
+        std::snprintf(path, sizeof(path), "%s", f);
+    else
+        std::snprintf(path, sizeof(path), "/tmp/lbm_b200_nccl_%ld_%s.id", (long)getppid(),
+                      std::getenv("MASTER_PORT") ? std::getenv("MASTER_PORT") : "0");
+    if (rr == 0) {
+        int rc = lbm_nccl_unique_id(id128);
+        if (rc) return rc;
+        std::string tmp = std::string(path) + ".tmp";
+        FILE* f = std::fopen(tmp.c_str(), "wb");
+        if (!f || std::fwrite(id128, 1, 128, f) != 128) {
+            if (f) std::fclose(f);
+            return fail(nullptr, LBM_ERR_IO, std::string("cannot write ") + tmp);
+        }
+        std::fclose(f);
+        if (std::rename(tmp.c_str(), path) != 0) return fail(nullptr, LBM_ERR_IO, std::string("cannot rename to ") + path);
+        g_id_file = path;  // removed once every rank has joined the communicator (create_common)
+        return LBM_OK;
+    }
+    for (int tries = 0; tries < 6000; ++tries) {  // up to 60 s
+        FILE* f = std::fopen(path, "rb");
+        if (f) {
+            const size_t n = std::fread(id128, 1, 128, f);
+            std::fclose(f);
+            if (n == 128) return LBM_OK;
+        }
+        usleep(10000);
+    }
+    return fail(nullptr, LBM_ERR_IO, std::string("timed out waiting for ") + path);
+}
+
+int lbm_set_params(lbm_handle h, const lbm_params* p) {
+    CHECK_H(h);
+    if (!p) return fail(h, LBM_ERR_INVALID, "null params");
+    if (p->nx != h->p.nx || p->ny != h->p.ny) return fail(h, LBM_ERR_INVALID, "nx / ny are fixed at creation");
+    if (!(p->tau > 0.5)) return fail(h, LBM_ERR_INVALID, "tau must exceed 0.5");
+    if (((p->flags ^ h->p.flags) & (LBM_FLAG_PERIODIC_X | LBM_FLAG_PERIODIC_Y)) != 0)
+        return fail(h, LBM_ERR_INVALID, "periodicity is fixed at creation");
+    h->p = *p;
+    h->cyl_x = static_cast<int>(p->cylinder_x * p->nx);
+    h->cyl_y = static_cast<int>(p->cylinder_y * p->ny);
+    h->cyl_r = static_cast<int>(p->cylinder_radius * p->ny);
+    h->bc.u_in = p->inlet_velocity;
+    return LBM_OK;
+}
+
+int lbm_allreduce(lbm_handle h, double* v, int n, int op) {
+    CHECK_H(h);
+    if (!v || n < 0 || n > LBM_REDUCE_MAX || op < LBM_SUM || op > LBM_MAX) return fail(h, LBM_ERR_INVALID, "bad argument");
+    if (!h->comm || n == 0) return LBM_OK;  // one slab: the local value is the global one
+    CU(h, cudaSetDevice(h->device));
+    const ncclRedOp_t o = op == LBM_SUM ? ncclSum : (op == LBM_MIN ? ncclMin : ncclMax);
+    CU(h, cudaMemcpyAsync(h->d_red, v, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    NC(h, nccl_api().AllReduce(h->d_red, h->d_red, n, ncclDouble, o, h->comm, h->stream));
+    CU(h, cudaMemcpyAsync(v, h->d_red, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return LBM_OK;
+}
+
+int lbm_gather_macros(lbm_handle h, double* rho, double* ux, double* uy) {
+    CHECK_H(h);
+    CU(h, cudaSetDevice(h->device));
+    int rc = ensure_macros(h);
+    if (rc) return rc;
+    const Layout& L = h->L;
+    const size_t slab = (size_t)L.lnx * L.ny;
+    double* host[3] = {rho, ux, uy};
+    double* dev[3] = {h->d_rho, h->d_ux, h->d_uy};
+    if (h->world == 1) return lbm_download_macros(h, rho, ux, uy);
+    const NcclApi& N = nccl_api();
+    if (h->rank != 0) {
+        for (int k = 0; k < 3; ++k) NC(h, N.Send(dev[k], slab, ncclDouble, 0, h->comm, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        return LBM_OK;
+    }
+    if (!rho || !ux || !uy) return fail(h, LBM_ERR_INVALID, "rank 0 needs all three output arrays");
+    if (!h->d_gather) CU(h, cudaMalloc(&h->d_gather, slab * sizeof(double)));
+    const size_t dpitch = (size_t)L.gnx * sizeof(double), spitch = (size_t)L.lnx * sizeof(double);
+    for (int k = 0; k < 3; ++k)  // own slab: rows of lnx doubles into rows of gnx
+        CU(h, cudaMemcpy2DAsync(host[k], dpitch, dev[k], spitch, spitch, L.ny, cudaMemcpyDeviceToHost, h->stream));
+    for (int r = 1; r < h->world; ++r)
+        for (int k = 0; k < 3; ++k) {
+            NC(h, N.Recv(h->d_gather, slab, ncclDouble, r, h->comm, h->stream));
+            CU(h, cudaMemcpy2DAsync(host[k] + (size_t)r * L.lnx, dpitch, h->d_gather, spitch, spitch, L.ny,
+                                    cudaMemcpyDeviceToHost, h->stream));
+        }
+    CU(h, cudaStreamSynchronize(h->stream));
     return LBM_OK;
 }
 

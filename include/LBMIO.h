@@ -1,0 +1,435 @@
+// LBMIO.h -- LBM::IOManager with the reference's public surface and file formats (its
+// include/LBMIO.h:35, 55, 114, 194): forces.csv, vtk_output/lbm_%06d.vtk, velocity_field.csv,
+// simulation_params.csv, byte-compatible so that scripts/lift.py and
+// scripts/visualise_results.py keep working.
+//
+// What changed underneath:
+//   * the momentum-exchange sum runs on the GPU over a precomputed link list (k_forces); the
+//     MPI_Reduce pair of :167-168 is one NCCL all-reduce (lbm_allreduce);
+//   * fields reach the host through lbm_gather_macros (one pinned image, slabs copied with
+//     strided D2H) instead of MPI_Gather + 3 x MPI_Gatherv (:225-300);
+//   * VTK frames can leave asynchronously (FrameWriter): a pinned double buffer filled by
+//     lbm_snapshot_begin_slot on the copy stream, formatted and written by a host thread while
+//     the GPU keeps stepping;
+//   * decimal formatting is done by an exact "%.8f" routine spread over the host cores (the
+//     reference's iostream writer needs ~2 s for a 50 MB frame).
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <fstream>
+#include <functional>
+#include <iomanip>
+#include <iostream>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "LBMConfig.h"
+#include "LBMGrid.h"
+#include "lbm_b200.h"
+
+namespace LBM {
+
+namespace textio {
+
+// Writes v exactly as printf("%.8f") / std::fixed << std::setprecision(8) would (correctly
+// rounded, ties to even, sign of zero kept) and returns the number of characters (at most
+// FIXED8_MAX).  Fast path for |v| < 1e15: the integer part is exact, and the fraction times 1e8
+// is split into a double product and its exact FMA error term, which decides the rounding of
+// the 8th decimal without big-number arithmetic.
+constexpr int FIXED8_MAX = 336;  // "-" + 309 digits + "." + 8 digits, rounded up
+
+inline int fixed8(double v, char* out) {
+    const double a = std::fabs(v);
+    if (!(a < 1e15)) return std::snprintf(out, FIXED8_MAX, "%.8f", v);  // huge, inf, nan: the slow exact path
+    const double whole = std::floor(a);
+    const double fr = a - whole;  // exact, in [0, 1)
+    const double hi = fr * 1e8;
+    const double lo = std::fma(fr, 1e8, -hi);  // fr*1e8 == hi + lo exactly, |lo| <= ulp(hi)/2 << 0.5
+    const double r = std::floor(hi);
+    const double frac = hi - r;  // exact
+    uint64_t ip = (uint64_t)whole;
+    uint32_t fp = (uint32_t)r;
+    // frac is a multiple of ulp(hi) and so is 0.5: unless frac == 0.5 the tiny lo cannot change
+    // the side; at frac == 0.5 the sign of lo decides, and an exact tie goes to the even digit.
+    // (frac == 0 with lo < 0 is r - eps, which still rounds to r.)
+    if (frac > 0.5 || (frac == 0.5 && (lo > 0.0 || (lo == 0.0 && (fp & 1u))))) {
+        if (++fp == 100000000u) {
+            fp = 0;
+            ++ip;
+        }
+    }
+    char* p = out;
+    if (std::signbit(v)) *p++ = '-';
+    char tmp[24];
+    int k = 0;
+    do {
+        tmp[k++] = (char)('0' + ip % 10);
+        ip /= 10;
+    } while (ip);
+    while (k) *p++ = tmp[--k];
+    *p++ = '.';
+    for (int d = 7; d >= 0; --d) {
+        p[d] = (char)('0' + fp % 10);
+        fp /= 10;
+    }
+    p += 8;
+    return (int)(p - out);
+}
+
+inline int integer(long long v, char* out) { return std::snprintf(out, 24, "%lld", v); }
+
+// Formats items [0, n) with `fmt(index, char*) -> chars written` (at most max_chars_per_item
+// each) on several host threads, block by block so that memory stays bounded, and writes the
+// blocks to `f` in order.
+inline void parallel_emit(std::FILE* f, size_t n, size_t max_chars_per_item,
+                          const std::function<int(size_t, char*)>& fmt) {
+    const size_t block = 1u << 20;
+    unsigned hw = std::thread::hardware_concurrency();
+    const unsigned nthreads = std::max(1u, std::min(hw ? hw : 1u, 16u));
+    std::vector<std::vector<char>> bufs(nthreads);
+    std::vector<size_t> used(nthreads);
+    for (size_t b0 = 0; b0 < n; b0 += block) {
+        const size_t b1 = std::min(n, b0 + block), per = (b1 - b0 + nthreads - 1) / nthreads;
+        auto work = [&](unsigned t) {
+            const size_t lo = std::min(b1, b0 + t * per), hi = std::min(b1, lo + per);
+            std::vector<char>& buf = bufs[t];
+            if (buf.size() < (hi - lo) * 48 + max_chars_per_item) buf.resize((hi - lo) * 48 + max_chars_per_item);
+            size_t pos = 0;
+            for (size_t k = lo; k < hi; ++k) {
+                if (buf.size() - pos < max_chars_per_item) buf.resize(buf.size() * 2 + max_chars_per_item);
+                pos += (size_t)fmt(k, buf.data() + pos);
+            }
+            used[t] = pos;
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(work, t);
+        work(0);
+        for (auto& th : pool) th.join();
+        for (unsigned t = 0; t < nthreads; ++t) std::fwrite(bufs[t].data(), 1, used[t], f);
+    }
+}
+
+}  // namespace textio
+
+class IOManager {
+   public:
+    IOManager() {
+        int world = 1;
+        lbm_bootstrap_env(&mpi_rank_, &world, nullptr, nullptr);
+        if (mpi_rank_ == 0) {
+            force_file_ = std::fopen("forces.csv", "w");
+            if (force_file_)
+                std::fputs("timestep,drag_force,lift_force,drag_coeff,lift_coeff\n", force_file_);
+            else
+                std::cerr << "ERROR: Could not open forces.csv\n";
+        }
+    }
+    ~IOManager() {
+        if (force_file_) std::fclose(force_file_);
+    }
+    IOManager(const IOManager&) = delete;
+    IOManager& operator=(const IOManager&) = delete;
+
+    // Momentum-exchange forces of the CURRENT post-collision state (reference :114-192): GPU link
+    // reduction per slab, summed over slabs, one CSV row on rank 0.
+    void record_forces(int timestep, const Grid& grid, const SimulationParams& params) {
+        double f[2] = {0.0, 0.0};
+        grid.check(lbm_get_forces(grid.handle(), &f[0], &f[1]));
+        grid.check(lbm_allreduce(grid.handle(), f, 2, LBM_SUM));
+        write_force_row(timestep, f[0], f[1], params);
+    }
+
+    // One forces.csv row from already reduced force components (Solver::run's fast path: the
+    // rows come out of lbm_run).  Format and coefficients: reference :171-190.
+    void write_force_row(int timestep, double fx, double fy, const SimulationParams& params) {
+        if (mpi_rank_ != 0 || !force_file_) return;
+        const double D_ref = 2.0 * params.get_cylinder_radius_cells();
+        const double q_ref = 0.5 * 1.0 * params.inlet_velocity * params.inlet_velocity * D_ref;
+        const double cd = (q_ref > 1e-12) ? fx / q_ref : 0.0;
+        const double cl = (q_ref > 1e-12) ? fy / q_ref : 0.0;
+        char line[4 * textio::FIXED8_MAX + 64], *p = line;
+        p += textio::integer(timestep, p);
+        for (double v : {fx, fy, cd, cl}) {
+            *p++ = ',';
+            p += textio::fixed8(v, p);
+        }
+        *p++ = '\n';
+        std::fwrite(line, 1, (size_t)(p - line), force_file_);
+        if (timestep % 10000 == 0) std::fflush(force_file_);
+    }
+
+    // ASCII legacy VTK, reference :55-111, byte for byte.
+    static void write_vtk_timestep(const std::vector<double>& ux_g, const std::vector<double>& uy_g,
+                                   const std::vector<double>& rho_g, const SimulationParams& p, int timestep) {
+        write_vtk_arrays(ux_g.data(), uy_g.data(), rho_g.data(), p.nx, p.ny, timestep);
+    }
+
+    static void write_vtk_arrays(const double* ux, const double* uy, const double* rho, int nx, int ny, int timestep) {
+        char filename[256];
+        std::snprintf(filename, sizeof(filename), "vtk_output/lbm_%06d.vtk", timestep);
+        std::FILE* f = std::fopen(filename, "w");
+        if (!f) {
+            std::cerr << "ERROR: Cannot write " << filename << "\n";
+            return;
+        }
+        std::vector<char> big(1 << 22);
+        std::setvbuf(f, big.data(), _IOFBF, big.size());
+        std::fprintf(f, "# vtk DataFile Version 3.0\nLBM Flow Timestep %d\nASCII\nDATASET STRUCTURED_POINTS\n", timestep);
+        std::fprintf(f, "DIMENSIONS %d %d 1\nORIGIN 0 0 0\nSPACING 1 1 1\nPOINT_DATA %d\n", nx, ny, nx * ny);
+        const size_t n = (size_t)nx * ny;
+        std::fputs("VECTORS velocity double\n", f);
+        textio::parallel_emit(f, n, 2 * textio::FIXED8_MAX + 16, [&](size_t k, char* o) {
+            char* q = o;
+            q += textio::fixed8(ux[k], q);
+            *q++ = ' ';
+            q += textio::fixed8(uy[k], q);
+            std::memcpy(q, " 0.0\n", 5);
+            return (int)(q + 5 - o);
+        });
+        std::fputs("\nSCALARS velocity_magnitude double\nLOOKUP_TABLE default\n", f);
+        textio::parallel_emit(f, n, textio::FIXED8_MAX + 16, [&](size_t k, char* o) {
+            int c = textio::fixed8(std::sqrt(ux[k] * ux[k] + uy[k] * uy[k]), o);
+            o[c] = '\n';
+            return c + 1;
+        });
+        std::fputs("\nSCALARS density double\nLOOKUP_TABLE default\n", f);
+        textio::parallel_emit(f, n, textio::FIXED8_MAX + 16, [&](size_t k, char* o) {
+            int c = textio::fixed8(rho[k], o);
+            o[c] = '\n';
+            return c + 1;
+        });
+        std::fclose(f);
+    }
+
+    // velocity_field.csv, simulation_params.csv and the force-coefficient summary (reference
+    // :194-219).  forces.csv is flushed first so that every row takes part in the averages (the
+    // reference re-reads the file while its stream is still buffered, :367-372).
+    void write_final_results(const Grid& grid, const SimulationParams& params) {
+        if (mpi_rank_ == 0) std::cout << "\nGathering final results..." << std::endl;
+        std::vector<double> g_rho, g_ux, g_uy;
+        if (mpi_rank_ == 0) {
+            const size_t n = (size_t)grid.global_nx() * grid.global_ny();
+            g_rho.resize(n);
+            g_ux.resize(n);
+            g_uy.resize(n);
+        }
+        grid.check(lbm_gather_macros(grid.handle(), g_rho.data(), g_ux.data(), g_uy.data()));
+        if (mpi_rank_ == 0) {
+            write_velocity_field(g_ux, g_uy, g_rho, params);
+            write_simulation_params(g_ux, g_uy, params);
+            if (force_file_) std::fflush(force_file_);
+            calculate_time_averaged_drag();
+            std::cout << "Files written: velocity_field.csv, simulation_params.csv, forces.csv" << std::endl;
+        }
+        double token = 0.0;  // MPI_Barrier of :218
+        grid.check(lbm_allreduce(grid.handle(), &token, 1, LBM_SUM));
+    }
+
+    int rank() const { return mpi_rank_; }
+
+   private:
+    static void write_velocity_field(const std::vector<double>& ux_g, const std::vector<double>& uy_g,
+                                     const std::vector<double>& rho_g, const SimulationParams& p) {
+        std::FILE* f = std::fopen("velocity_field.csv", "w");
+        if (!f) {
+            std::cerr << "ERROR: Cannot write velocity_field.csv\n";
+            return;
+        }
+        std::vector<char> big(1 << 22);
+        std::setvbuf(f, big.data(), _IOFBF, big.size());
+        std::fputs("x,y,ux,uy,rho,velocity_magnitude\n", f);
+        const int nx = p.nx;
+        textio::parallel_emit(f, (size_t)p.nx * p.ny, 4 * textio::FIXED8_MAX + 64, [&](size_t k, char* o) {
+            char* q = o;
+            q += textio::integer((long long)(k % nx), q);
+            *q++ = ',';
+            q += textio::integer((long long)(k / nx), q);
+            const double mag = std::sqrt(ux_g[k] * ux_g[k] + uy_g[k] * uy_g[k]);
+            for (double v : {ux_g[k], uy_g[k], rho_g[k], mag}) {
+                *q++ = ',';
+                q += textio::fixed8(v, q);
+            }
+            *q++ = '\n';
+            return (int)(q - o);
+        });
+        std::fclose(f);
+        std::cout << "  velocity_field.csv written\n";
+    }
+
+    static void write_simulation_params(const std::vector<double>& ux_g, const std::vector<double>& uy_g,
+                                        const SimulationParams& p) {
+        std::ofstream file("simulation_params.csv");
+        if (!file) {
+            std::cerr << "ERROR: Cannot write simulation_params.csv\n";
+            return;
+        }
+        double max_vel = 0.0, avg_vel = 0.0;  // serial, row-major: the reference's summation order (:339-346)
+        const size_t n = (size_t)p.nx * p.ny;
+        for (size_t k = 0; k < n; ++k) {
+            const double vel = std::sqrt(ux_g[k] * ux_g[k] + uy_g[k] * uy_g[k]);
+            max_vel = std::max(max_vel, vel);
+            avg_vel += vel;
+        }
+        avg_vel /= (p.nx * p.ny);
+        file << "parameter,value\n"
+             << "nx," << p.nx << "\n"
+             << "ny," << p.ny << "\n"
+             << "tau," << std::fixed << std::setprecision(8) << p.tau << "\n"
+             << "nu," << p.nu() << "\n"
+             << "inlet_velocity," << p.inlet_velocity << "\n"
+             << "num_timesteps," << p.num_timesteps << "\n"
+             << "reynolds_number," << p.reynolds() << "\n"
+             << "cylinder_x," << p.get_cylinder_x() << "\n"
+             << "cylinder_y," << p.get_cylinder_y() << "\n"
+             << "cylinder_radius," << p.get_cylinder_radius_cells() << "\n"
+             << "max_velocity," << max_vel << "\n"
+             << "avg_velocity," << avg_vel << "\n";
+        std::cout << "  simulation_params.csv written\n";
+    }
+
+    // Mean and range of C_D / C_L over the rows with timestep > 1000 (reference :367-413).
+    static void calculate_time_averaged_drag() {
+        std::ifstream in("forces.csv");
+        if (!in) {
+            std::cerr << "Warning: Could not read forces.csv for averaging\n";
+            return;
+        }
+        std::string line;
+        std::getline(in, line);  // header
+        double sum_cd = 0.0, sum_cl = 0.0, max_cd = -1e9, min_cd = 1e9, max_cl = -1e9, min_cl = 1e9;
+        int count = 0;
+        while (std::getline(in, line)) {
+            int t;
+            double fx, fy, cd, cl;
+            if (std::sscanf(line.c_str(), "%d,%lf,%lf,%lf,%lf", &t, &fx, &fy, &cd, &cl) != 5 || t <= 1000) continue;
+            sum_cd += cd;
+            sum_cl += cl;
+            max_cd = std::max(max_cd, cd);
+            min_cd = std::min(min_cd, cd);
+            max_cl = std::max(max_cl, cl);
+            min_cl = std::min(min_cl, cl);
+            ++count;
+        }
+        if (count == 0) return;
+        std::cout << "\n=== Time-Averaged Force Coefficients ===\n";
+        std::cout << "  Mean C_D = " << std::fixed << std::setprecision(6) << sum_cd / count << "\n";
+        std::cout << "  C_D range: [" << min_cd << ", " << max_cd << "]\n";
+        std::cout << "  Mean C_L = " << sum_cl / count << "\n";
+        std::cout << "  C_L range: [" << min_cl << ", " << max_cl << "]\n";
+        std::cout << "  (Averaged over " << count << " samples)\n";
+    }
+
+    std::FILE* force_file_ = nullptr;
+    int mpi_rank_ = 0;
+};
+
+// Asynchronous VTK output (replaces the blocking gather + write of the reference's
+// Solver::write_vtk_frame, include/LBMSolver.h:269-362).  Two pinned host images of rho/ux/uy;
+// frame k is copied into image k%2 on the engine's copy stream while the compute stream moves
+// on, and a writer thread formats it once its copy has landed.  submit() blocks only when both
+// images are still being written (the ASCII format, not the GPU, is then the bottleneck).
+class FrameWriter {
+   public:
+    explicit FrameWriter(const Grid& grid) : grid_(grid) {}
+    ~FrameWriter() { finish(); }
+
+    void submit(int timestep) {
+        const int slot = (int)(submitted_ % 2);
+        const size_t n = (size_t)grid_.global_nx() * grid_.global_ny();
+        {
+            std::unique_lock<std::mutex> lk(m_);
+            cv_.wait(lk, [&] { return !busy_[slot]; });
+        }
+        const bool root = grid_.mpi_rank() == 0;
+        if (root && !image_[slot]) {
+            void* p = nullptr;
+            grid_.check(lbm_host_alloc(&p, 3 * n * sizeof(double)));
+            image_[slot] = static_cast<double*>(p);
+        }
+        double* rho = root ? image_[slot] : nullptr;
+        double* ux = root ? image_[slot] + n : nullptr;
+        double* uy = root ? image_[slot] + 2 * n : nullptr;
+        bool wait_slot = false;
+        if (grid_.mpi_size() == 1) {
+            grid_.check(lbm_snapshot_begin_slot(grid_.handle(), slot, rho, ux, uy));  // returns at once
+            wait_slot = true;
+        } else {
+            grid_.check(lbm_gather_macros(grid_.handle(), rho, ux, uy));  // collective, synchronous
+        }
+        ++submitted_;
+        if (!root) return;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            busy_[slot] = true;
+            jobs_.push_back({timestep, slot, wait_slot});
+        }
+        if (!thread_.joinable()) thread_ = std::thread([this] { loop(); });
+        cv_.notify_all();
+    }
+
+    // Blocks until every submitted frame is on disk.
+    void finish() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        if (thread_.joinable()) thread_.join();
+        stop_ = false;
+        for (double*& p : image_)
+            if (p) {
+                lbm_host_free(p);
+                p = nullptr;
+            }
+    }
+
+    size_t frames_written() const { return written_; }
+
+   private:
+    struct Job {
+        int timestep, slot;
+        bool wait_slot;
+    };
+    void loop() {
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return stop_ || !jobs_.empty(); });
+                if (jobs_.empty()) return;
+                j = jobs_.front();
+                jobs_.pop_front();
+            }
+            if (j.wait_slot) lbm_snapshot_wait_slot(grid_.handle(), j.slot);
+            const size_t n = (size_t)grid_.global_nx() * grid_.global_ny();
+            const double* img = image_[j.slot];
+            IOManager::write_vtk_arrays(img + n, img + 2 * n, img, grid_.global_nx(), grid_.global_ny(), j.timestep);
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                busy_[j.slot] = false;
+                ++written_;
+            }
+            cv_.notify_all();
+        }
+    }
+
+    const Grid& grid_;
+    double* image_[2] = {nullptr, nullptr};
+    bool busy_[2] = {false, false};
+    std::deque<Job> jobs_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::thread thread_;
+    bool stop_ = false;
+    size_t submitted_ = 0, written_ = 0;
+};
+
+}  // namespace LBM

@@ -95,6 +95,16 @@ int lbm_destroy(lbm_handle h);
 const char* lbm_last_error(lbm_handle h); /* h may be NULL: error of the last failed create */
 int lbm_get_info(lbm_handle h, lbm_info* out);
 
+/* Rank discovery for a C++ driver started once per GPU by torchrun / mpirun / srun (used as
+ * plain process launchers): replaces MPI_Init + MPI_Comm_rank/size of src/main.cpp:8 and
+ * include/LBMGrid.h:58-59.  With world > 1 rank 0 creates the NCCL id and hands it to the other
+ * ranks of the same launch through a file in /tmp (single node).  Without a launcher: 0 of 1. */
+int lbm_bootstrap_env(int* rank, int* world, int* local_rank, void* nccl_unique_id_out128);
+/* Change tau / inlet velocity / cylinder / output_frequency / body force after creation (the
+ * reference's Grid is constructed from nx, ny alone and learns the rest in setup_geometry and
+ * initialise, include/LBMGrid.h:57,152,185).  nx, ny and periodicity cannot change. */
+int lbm_set_params(lbm_handle h, const lbm_params* p);
+
 /* ---- set-up: Solver::initialise (include/LBMSolver.h:31-41) ---- */
 int lbm_setup_geometry(lbm_handle h, int* solid_count); /* Grid::setup_geometry, LBMGrid.h:152-183 */
 int lbm_initialise(lbm_handle h, double inlet_u);       /* Grid::initialise,     LBMGrid.h:185-246 */
@@ -121,6 +131,19 @@ int lbm_check_stability(lbm_handle h, int* ok, int* first_bad_step);
 /* Grid::max_velocity (LBMGrid.h:319-344): slab-local sqrt(max(ux^2+uy^2)). */
 int lbm_max_velocity(lbm_handle h, double* out);
 
+/* The reference's scalar reductions over ranks -- MPI_Reduce(SUM) of the force components
+ * (LBMIO.h:167-168), MPI_Allreduce(MAX) of the velocity (LBMGrid.h:342), the solid count
+ * (LBMGrid.h:175) -- as one in-place NCCL all-reduce of up to LBM_REDUCE_MAX host doubles.
+ * Collective: every slab of the job must call it.  No-op for a single slab. */
+enum { LBM_SUM = 0, LBM_MIN = 1, LBM_MAX = 2 };
+#define LBM_REDUCE_MAX 64
+int lbm_allreduce(lbm_handle h, double* values, int n, int op);
+/* Solver::write_vtk_frame's gather (LBMSolver.h:269-362) and
+ * IOManager::gather_and_reconstruct_field (LBMIO.h:225-300): rho/ux/uy of every slab assembled on
+ * rank 0 as global row-major [y*global_nx + x] host arrays (peer slabs arrive over NCCL, then
+ * strided D2H copies).  Collective; the pointers are ignored on ranks other than 0. */
+int lbm_gather_macros(lbm_handle h, double* rho, double* ux, double* uy);
+
 /* ---- observable state: Grid accessors (include/LBMGrid.h:115-129,145) ---- */
 enum { LBM_F_CURRENT = 0, LBM_F_NEXT = 1 };
 int lbm_download_f(lbm_handle h, int which, double* aos_padded);
@@ -137,13 +160,19 @@ int lbm_upload_f(lbm_handle h, const double* f_current_aos_padded, int iteration
  * a copy stream; the compute stream only waits for the on-device macro kernel. */
 int lbm_snapshot_begin(lbm_handle h, double* rho, double* ux, double* uy);
 int lbm_snapshot_wait(lbm_handle h);
+/* The same with one completion event per slot, for a double-buffered writer thread:
+ * lbm_snapshot_wait_slot only synchronises on that event and may be called from a second host
+ * thread while the owning thread keeps stepping. */
+#define LBM_SNAPSHOT_SLOTS 4
+int lbm_snapshot_begin_slot(lbm_handle h, int slot, double* rho, double* ux, double* uy);
+int lbm_snapshot_wait_slot(lbm_handle h, int slot);
 int lbm_host_alloc(void** ptr, size_t bytes); /* cudaHostAlloc */
 int lbm_host_free(void* ptr);
 
 /* ---- measurement ---- */
 /* Run n_steps and time them with CUDA events on the compute stream.  ms_total covers the whole
  * region; ms_bulk is the summed duration of the bulk collide-stream kernel launches only
- * (events around each launch; use a small n_steps for that, it serialises the stream). */
+ * (per_kernel = n > 0: events around the bulk launch of every n-th iteration). */
 int lbm_time_steps(lbm_handle h, int n_steps, int per_kernel, float* ms_total, float* ms_bulk, int* launches);
 /* Kernel launches issued by this handle since creation; launches and lattice cells of the bulk
  * collide-stream kernel covered by ms_bulk of the last lbm_time_steps(per_kernel=1). */

@@ -1,0 +1,10 @@
+# ncu evidence for bench.py's default workload (one GPU). Usage: bash tools/ncu_round.sh <tag>
+TAG=${1:-r01}
+CMD="python bench.py --steps 20 --warmup 3 --no-cpu-baseline"
+$CMD > gpurun_out/${TAG}_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
+echo "launch list rc=$?"
+$CMD > gpurun_out/${TAG}_plain2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:k_bulk -s 5 -c 3 -f -o gpurun_out/${TAG}_bulk $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
+echo "full capture rc=$?"
+ls -la gpurun_out/
