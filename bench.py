@@ -257,6 +257,13 @@ def main():
         raise SystemExit("--gpus %d does not match WORLD_SIZE %d" % (args.gpus, world))
 
     cfg = workload(args.workload, args.gpus)
+    # stdout carries exactly one JSON line: anything libraries print there (NCCL's version banner,
+    # for one) is sent to stderr instead
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
 
     # ---------------------------------------------------------------- reference arm (CPU)
     if args.impl == "reference":
@@ -276,7 +283,7 @@ def main():
             "e2e": {"value": mlups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
         return 0
 
     # ---------------------------------------------------------------- B200 arm
@@ -428,7 +435,7 @@ def main():
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks,
             "stable": bool(ok), "roofline_whole_step_frac": value * 1e6 * BYTES_PER_UPDATE / 1e9 / args.gpus / peak,
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -44,7 +44,7 @@ struct lbm_solver {
     bool periodic_x = false, periodic_y = false;
 
     cudaStream_t stream = nullptr, copy_stream = nullptr, comm_stream = nullptr;
-    cudaEvent_t ev_macros = nullptr, ev_snapshot = nullptr, ev_edge = nullptr, ev_comm = nullptr;
+    cudaEvent_t ev_macros = nullptr, ev_snapshot = nullptr, ev_edge = nullptr, ev_comm = nullptr, ev_main = nullptr;
     bool snapshot_pending = false;
     cudaEvent_t ev_slot[LBM_SNAPSHOT_SLOTS] = {};  // completion of the D2H copies of lbm_snapshot_begin_slot
 
@@ -281,6 +281,7 @@ int step_one(lbm_handle h) {
     StepArgs a = step_args(h, h->f[h->cur], dst, h->iter - 1, 1);
     const bool multi = (h->west >= 0 || h->east >= 0);
     const bool split = multi && h->overlap && L.lnx >= 4;
+    bool edge_pending = false;  // this iteration's edge columns are still in flight on the comm stream
 
     auto bulk = [&](int x0, int x1) -> cudaError_t {
         if (h->time_bulk && (h->iter % h->time_bulk) == 0) {
@@ -300,22 +301,24 @@ int step_one(lbm_handle h) {
     };
 
     if (split) {
-        // Edge columns first, so that their halo can travel while the interior is computed.
-        // The previous exchange (comm stream) must have landed before the edges are pulled.
-        CU(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
-        CU(h, launch_bulk(BULK_VEC2, pull, a, h->stream, 0, 1));
-        CU(h, launch_bulk(BULK_VEC2, pull, a, h->stream, L.lnx - 1, L.lnx));
-        CU(h, launch_fixup(pull, a, h->bc, h->d_ring, h->n_ring_edge, h->d_solids, h->n_solid_edge, h->stream));
-        h->launches += 3;
-        CU(h, cudaEventRecord(h->ev_edge, h->stream));
-        CU(h, cudaStreamWaitEvent(h->comm_stream, h->ev_edge, 0));
+        // Two streams, no stream waits for the wire:
+        //   comm stream : [wait: interior of t-1 done] edge columns of t -> halo exchange of t
+        //   main stream : [wait: edge columns of t-1 done] interior columns of t, interior fix-up
+        // Only the edge kernel reads ghost columns, and it runs behind the previous exchange on
+        // the same stream; the interior kernel needs columns 0 and lnx-1 of the previous buffer
+        // (written by the previous edge kernel) but never a ghost column.
+        CU(h, cudaStreamWaitEvent(h->stream, h->ev_edge, 0));
+        CU(h, cudaStreamWaitEvent(h->comm_stream, h->ev_main, 0));
+        CU(h, launch_edge(pull, a, h->bc, h->d_mask, h->comm_stream));
+        CU(h, cudaEventRecord(h->ev_edge, h->comm_stream));
         int rc = exchange(h, dst, h->comm_stream);
         if (rc) return rc;
         CU(h, cudaEventRecord(h->ev_comm, h->comm_stream));
         CU(h, bulk(1, L.lnx - 1));
         CU(h, launch_fixup(pull, a, h->bc, h->d_ring + h->n_ring_edge, h->n_ring - h->n_ring_edge,
                            h->d_solids + h->n_solid_edge, h->n_solid - h->n_solid_edge, h->stream));
-        h->launches += 2;
+        h->launches += 3;
+        edge_pending = true;
     } else {
         CU(h, bulk(0, L.lnx));
         CU(h, launch_fixup(pull, a, h->bc, h->d_ring, h->n_ring, h->d_solids, h->n_solid, h->stream));
@@ -340,11 +343,13 @@ int step_one(lbm_handle h) {
             if (rc) return rc;
         }
         const int slot = (int)h->pending.size();
+        if (edge_pending) CU(h, cudaStreamWaitEvent(h->stream, h->ev_edge, 0));  // links may end in an edge column
         CU(h, launch_forces(dst, h->d_links, h->n_links, h->d_forces + 2 * slot, h->stream));
         h->launches += 1;
         h->pending.push_back({h->iter, slot});
     }
 
+    if (split) CU(h, cudaEventRecord(h->ev_main, h->stream));
     h->cur ^= 1;
     h->prev_is_next = h->cur_is_next;
     h->cur_is_next = true;
@@ -394,6 +399,7 @@ int check_pending(lbm_handle h) {
 int read_first_bad(lbm_handle h, int* out) {
     int v = INT_MAX;
     const int* src = h->d_first_bad;
+    if (h->west >= 0 || h->east >= 0) CU(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));  // edge kernels flag too
     if (h->comm) {
         NC(h, nccl_api().AllReduce(h->d_first_bad, h->d_first_bad_all, 1, ncclInt, ncclMin, h->comm, h->stream));
         src = h->d_first_bad_all;
@@ -469,6 +475,7 @@ int create_common(const lbm_params* p, int device, int rank, int world, const vo
     CUC(cudaEventCreateWithFlags(&h->ev_snapshot, cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&h->ev_edge, cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
+    CUC(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
     const size_t fbytes = (size_t)h->L.plane * Q * sizeof(double);
     CUC(cudaMalloc(&h->f[0], fbytes));
     CUC(cudaMalloc(&h->f[1], fbytes));
@@ -486,6 +493,8 @@ int create_common(const lbm_params* p, int device, int rank, int world, const vo
     CUC(cudaMemcpyAsync(h->d_first_bad, &big, sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CUC(cudaStreamSynchronize(h->stream));
     CUC(cudaEventRecord(h->ev_comm, h->comm_stream));
+    CUC(cudaEventRecord(h->ev_edge, h->comm_stream));
+    CUC(cudaEventRecord(h->ev_main, h->stream));
 #undef CUC
     if (world > 1) {
         const NcclApi& N = nccl_api();
@@ -568,6 +577,7 @@ int lbm_destroy(lbm_handle h) {
     if (h->ev_snapshot) cudaEventDestroy(h->ev_snapshot);
     if (h->ev_edge) cudaEventDestroy(h->ev_edge);
     if (h->ev_comm) cudaEventDestroy(h->ev_comm);
+    if (h->ev_main) cudaEventDestroy(h->ev_main);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
@@ -605,6 +615,8 @@ int lbm_setup_geometry(lbm_handle h, int* solid_count) {
 int lbm_initialise(lbm_handle h, double inlet_u) {
     CHECK_H(h);
     CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->comm_stream));  // nothing of an earlier run may still touch the buffers
+    CU(h, cudaStreamSynchronize(h->stream));
     h->init_u = inlet_u;
     equilibrium_init(1.0, inlet_u, 0.0, h->bc.e);
     const int wz = (!h->periodic_x && h->rank == 0) ? 1 : 0;
@@ -703,6 +715,7 @@ int lbm_get_forces(lbm_handle h, double* fx, double* fy) {
     CU(h, cudaSetDevice(h->device));
     int rc = drain_forces(h);
     if (rc) return rc;
+    if (h->west >= 0 || h->east >= 0) CU(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
     CU(h, launch_forces(h->f[h->cur], h->d_links, h->n_links, h->d_forces, h->stream));
     h->launches += 1;
     double v[2];
@@ -786,6 +799,7 @@ int lbm_upload_f(lbm_handle h, const double* aos, int iteration) {
     if (rc) return rc;
     rc = drain_forces(h);
     if (rc) return rc;
+    CU(h, cudaStreamSynchronize(h->comm_stream));
     const size_t n = (size_t)(h->L.lnx + 2) * (h->L.ny + 2) * Q * sizeof(double);
     CU(h, cudaMemcpyAsync(h->d_scratch, aos, n, cudaMemcpyHostToDevice, h->stream));
     h->cur = 0;

@@ -144,6 +144,36 @@ __global__ void __launch_bounds__(128) k_fixup(StepArgs a, BcArgs b, int pull, c
 }
 
 // ------------------------------------------------------------------------------------------
+// The two slab-edge columns (x = 0 and x = lnx-1) of a multi-slab job, every rule in one launch:
+// solid cells keep w, fluid cells are pulled, get the wall / inlet / outlet rule that applies to
+// them, are checked, collided and stored.  Runs on the communication stream ahead of the halo
+// exchange while the bulk kernel works on the interior columns (lbm_engine.cu: step_one).
+__global__ void __launch_bounds__(128) k_edge(StepArgs a, BcArgs b, const unsigned char* __restrict__ mask, int pull) {
+    const Layout& L = a.L;
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= L.ny) return;
+    const int x = blockIdx.y == 0 ? 0 : L.lnx - 1;
+    if (mask[L.at(x + 1, y)]) {
+        if (a.write) store_cell(a.dst, L, x + 1, y, b.w);
+        return;
+    }
+    double f[Q];
+    if (pull) {
+        load_cell<true>(a.src, L, x + 1, y, f);
+        double rho_bc, u_out;
+        apply_bc(f, x, y, L, b, rho_bc, u_out);
+        if (any_unstable(f)) atomicMin(a.first_bad, a.bad_iter);
+    } else {
+        load_cell<false>(a.src, L, x + 1, y, f);
+    }
+    if (a.forced)
+        collide_cell<true>(f, a.tau_inv, a.Fx, a.Fy);
+    else
+        collide_cell<false>(f, a.tau_inv, 0.0, 0.0);
+    if (a.write) store_cell(a.dst, L, x + 1, y, f);
+}
+
+// ------------------------------------------------------------------------------------------
 // Momentum exchange: F = sum over links 2 c_i f_next(fluid, i)  (include/LBMIO.h:123-160).
 // The reference accumulates ONE running sum per component in (y, x, i) order over the solid
 // cells; the link list is built in that order, so adding the terms one after the other gives the
@@ -451,6 +481,12 @@ cudaError_t launch_fixup(bool pull, const StepArgs& a, const BcArgs& b, const in
     const long long n = (long long)n_ring + n_solid;
     if (n == 0) return cudaSuccess;
     k_fixup<<<cdiv(n, 128), 128, 0, s>>>(a, b, pull ? 1 : 0, ring, n_ring, solids, n_solid);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_edge(bool pull, const StepArgs& a, const BcArgs& b, const unsigned char* mask, cudaStream_t s) {
+    dim3 grid(cdiv(a.L.ny, 128), a.L.lnx > 1 ? 2 : 1);
+    k_edge<<<grid, 128, 0, s>>>(a, b, mask, pull ? 1 : 0);
     return cudaGetLastError();
 }
 

@@ -42,6 +42,9 @@ cudaError_t launch_bulk(int variant, bool pull, const StepArgs& a, cudaStream_t 
 cudaError_t launch_fixup(bool pull, const StepArgs& a, const BcArgs& b, const int2* ring, int n_ring,
                          const int2* solids, int n_solid, cudaStream_t s);
 
+// Both slab-edge columns in one launch (multi-slab jobs): pull, boundary rules, collide; solids = w.
+cudaError_t launch_edge(bool pull, const StepArgs& a, const BcArgs& b, const unsigned char* mask, cudaStream_t s);
+
 // Momentum-exchange reduction (reference include/LBMIO.h:114-162) over a precomputed link list.
 cudaError_t launch_forces(const double* f_next, const Link* links, int n_links, double* out_fx_fy, cudaStream_t s);
 
