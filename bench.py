@@ -238,6 +238,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="slab", choices=["slab", "c3", "c4", "c1"])
     ap.add_argument("--variant", type=int, default=None, help="bulk kernel variant (default: engine default)")
+    ap.add_argument("--aa", action="store_true", help="in-place AA variant: one population buffer (single GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -257,6 +258,8 @@ def main():
         raise SystemExit("--gpus %d does not match WORLD_SIZE %d" % (args.gpus, world))
 
     cfg = workload(args.workload, args.gpus)
+    if args.aa:
+        cfg["flags"] |= 16  # LBM_FLAG_AA
     # stdout carries exactly one JSON line: anything libraries print there (NCCL's version banner,
     # for one) is sent to stderr instead
     json_fd = os.dup(1)
@@ -369,6 +372,11 @@ def main():
                 "bytes_per_launch": (bulk_cells / bulk_launches) * BYTES_PER_UPDATE, "avg_launch_ms": bulk_ms,
                 "launches_timed": bulk_launches, "kernel_share_of_step": bulk_ms * args.steps / ms_total, "peak_source": peak_src,
                 "whole_step_frac": value * 1e6 * BYTES_PER_UPDATE / 1e9 / args.gpus / peak}
+        if args.aa:
+            # BASELINE.json quotes "72 B for AA" (the resident footprint per cell); an AA update still
+            # moves 9 loads + 9 stores = 144 B, which is what `achieved` counts
+            roof["kernel"] = "k_aa_even / k_aa_odd (in-place collide-stream)"
+            roof["frac_if_72B_per_update"] = roof["frac"] / 2
     else:
         roof = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None}
 
@@ -428,7 +436,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": cfg["label"], "nx": cfg["nx"], "ny": cfg["ny"], "tau": cfg["tau"],
                        "inlet_velocity": cfg["inlet_velocity"], "output_frequency": cfg["output_frequency"],
-                       "layout": "fp64 SoA, A-B double buffer", "kernel_variant": info.kernel_variant,
+                       "layout": "fp64 SoA, in-place AA pattern (one buffer)" if args.aa else "fp64 SoA, A-B double buffer", "kernel_variant": info.kernel_variant,
                        "partition": "x-slab x%d, NCCL send/recv halo (3 populations per face)" % world if world > 1 else "single GPU",
                        "l2": "inputs_exceed_l2 (%.2f GB per population buffer)" % (info.bytes_per_buffer / 1e9)
                        if info.bytes_per_buffer > 200e6 else "L2-resident working set (not roofline evidence)"},

@@ -19,6 +19,7 @@ FLAG_PERIODIC_X = 1
 FLAG_PERIODIC_Y = 2
 FLAG_NO_CYLINDER = 4
 FLAG_SHEAR_WAVE_INIT = 8
+FLAG_AA = 16
 
 F_CURRENT, F_NEXT = 0, 1
 VARIANT_SCALAR, VARIANT_VEC2, VARIANT_TMA = 0, 1, 2

@@ -75,6 +75,14 @@ struct lbm_solver {
     struct ForceRow { int t; double fx, fy; };
     std::vector<ForceRow> force_log;
 
+    // in-place AA variant (LBM_FLAG_AA): one buffer f[0]; see lbm_aa.cu
+    bool aa = false;
+    int aa_phase = 0;  // 0 natural layout, 1 reversed layout
+    AaFill* d_fills = nullptr;
+    int n_fill = 0;
+    Link *d_links_rev = nullptr, *d_links_nat = nullptr;  // link offsets in the reversed / pushed-natural layouts
+    double* d_ring_out = nullptr;
+
     BcArgs bc{};
     double init_u = 0.0;
     int variant = BULK_VEC2;
@@ -149,6 +157,46 @@ ObserveArgs observe_args(lbm_handle h) {
     return o;
 }
 
+AaArgs aa_args(lbm_handle h, int first) {
+    AaArgs a;
+    a.f = h->f[0];
+    a.L = h->L;
+    a.tau_inv = 1.0 / h->p.tau;
+    a.Fx = h->p.body_force_x;
+    a.Fy = h->p.body_force_y;
+    a.forced = (a.Fx != 0.0 || a.Fy != 0.0) ? 1 : 0;
+    a.first_bad = h->d_first_bad;
+    a.bad_iter = h->iter - 1;
+    a.first = first;
+    a.skip_rows = h->bc.walls;
+    a.x_begin = h->bc.inlet ? 1 : 0;
+    a.x_end = h->bc.outlet ? h->L.lnx - 1 : h->L.lnx;
+    a.variant = h->variant;
+    return a;
+}
+
+AaObserve aa_observe(lbm_handle h) {
+    AaObserve o;
+    o.f = h->f[0];
+    o.L = h->L;
+    o.mask = h->d_mask;
+    o.bc = h->bc;
+    o.phase = h->aa_phase;
+    o.cur_is_next = h->cur_is_next;
+    o.fresh = h->fresh;
+    o.ring_out = h->d_ring_out;
+    o.periodic_x = h->periodic_x;
+    o.periodic_y = h->periodic_y;
+    o.west_zero = h->periodic_x ? 0 : 1;
+    o.east_zero = h->periodic_x ? 0 : 1;
+    o.shear_wave = (h->p.flags & LBM_FLAG_SHEAR_WAVE_INIT) ? 1 : 0;
+    o.u0 = h->init_u;
+    o.tau_inv = 1.0 / h->p.tau;
+    o.Fx = h->p.body_force_x;
+    o.Fy = h->p.body_force_y;
+    return o;
+}
+
 // Geometry on the host: mask over the padded slab in GLOBAL coordinates (reference
 // include/LBMGrid.h:159-172), the solid list, the boundary-ring list and the momentum-exchange
 // link list (include/LBMIO.h:123-160; a link is owned by the slab that owns its fluid end, so
@@ -168,7 +216,7 @@ int build_geometry(lbm_handle h) {
         return dist_sq <= h->cyl_r * h->cyl_r;
     };
     std::vector<int2> solids, ring;
-    std::vector<Link> links;
+    std::vector<Link> links, links_rev, links_nat;
     for (int gx = 0; gx < L.lnx + 2; ++gx)
         for (int y = -1; y <= L.ny; ++y) {
             const bool s = solid_global(L.x_start + gx - 1, y);
@@ -214,11 +262,57 @@ int build_geometry(lbm_handle h) {
                     l.cx2 = 2 * cxi(i);
                     l.cy2 = 2 * cyi(i);
                     links.push_back(l);
+                    if (h->aa) {
+                        // the same link in the reversed layout (A[fluid][opp(i)]) and in the natural
+                        // layout after an O-step, where the population has been pushed into the solid
+                        // cell itself (through the reverse wrap if it crossed a periodic edge)
+                        l.off = (long long)oppi(i) * L.plane + L.at(fx + 1, fy);
+                        links_rev.push_back(l);
+                        const int sx = ((x % L.lnx) + L.lnx) % L.lnx;
+                        l.off = (long long)i * L.plane + L.at(sx + 1, y);
+                        links_nat.push_back(l);
+                    }
                 }
             }
         }
+    std::vector<AaFill> fills;
+    if (h->aa) {
+        // slots of fluid cells that no cell pushes into during an O-step
+        for (int x = 0; x < L.lnx; ++x)
+            for (int y = 0; y < L.ny; ++y) {
+                if (h->h_mask[L.at(x + 1, y)]) continue;
+                for (int i = 1; i < Q; ++i) {
+                    const int nx_ = x - cxi(i), ny_ = y - cyi(i);
+                    const bool out_x = !h->periodic_x && (nx_ < 0 || nx_ >= L.lnx);
+                    const bool out_y = !h->periodic_y && (ny_ < 0 || ny_ >= L.ny);
+                    AaFill e;
+                    e.off = (long long)i * L.plane + L.at(x + 1, y);
+                    e.i = i;
+                    if (out_y) e.kind = 2;                                  // S/N ghost rows and corners: eq(1,u_in,0)
+                    else if (out_x) e.kind = 1;                             // W/E ghost columns: 0.0
+                    else if (h->h_mask[L.at(nx_ + 1, ny_)]) e.kind = 0;     // solid neighbour: w
+                    else continue;
+                    fills.push_back(e);
+                }
+            }
+    }
     cudaFree(h->d_ring); cudaFree(h->d_solids); cudaFree(h->d_links);
+    cudaFree(h->d_fills); cudaFree(h->d_links_rev); cudaFree(h->d_links_nat);
     h->d_ring = nullptr; h->d_solids = nullptr; h->d_links = nullptr;
+    h->d_fills = nullptr; h->d_links_rev = nullptr; h->d_links_nat = nullptr;
+    if (h->aa && links_rev.size() != links.size())
+        return fail(h, LBM_ERR_INVALID, "internal: link lists of the two buffer schemes disagree");
+    h->n_fill = (int)fills.size();
+    if (!fills.empty()) {
+        CU(h, cudaMalloc(&h->d_fills, sizeof(AaFill) * fills.size()));
+        CU(h, cudaMemcpyAsync(h->d_fills, fills.data(), sizeof(AaFill) * fills.size(), cudaMemcpyHostToDevice, h->stream));
+    }
+    if (!links_rev.empty()) {
+        CU(h, cudaMalloc(&h->d_links_rev, sizeof(Link) * links_rev.size()));
+        CU(h, cudaMalloc(&h->d_links_nat, sizeof(Link) * links_nat.size()));
+        CU(h, cudaMemcpyAsync(h->d_links_rev, links_rev.data(), sizeof(Link) * links_rev.size(), cudaMemcpyHostToDevice, h->stream));
+        CU(h, cudaMemcpyAsync(h->d_links_nat, links_nat.data(), sizeof(Link) * links_nat.size(), cudaMemcpyHostToDevice, h->stream));
+    }
     h->n_ring = (int)ring.size();
     h->n_solid = (int)solids.size();
     h->n_links = (int)links.size();
@@ -273,8 +367,71 @@ int exchange(lbm_handle h, double* buf, cudaStream_t s) {
     return LBM_OK;
 }
 
+const Link* aa_links(lbm_handle h) {
+    if (!h->cur_is_next) return h->d_links;  // fresh: f_next == f_current, natural addressing
+    return h->aa_phase == 1 ? h->d_links_rev : h->d_links_nat;
+}
+
+// One reference iteration in the single-buffer variant: E-step from the natural layout, O-step
+// from the reversed one (lbm_aa.cu).
+int step_one_aa(lbm_handle h) {
+    const Layout& L = h->L;
+    const bool odd = h->aa_phase == 1;
+    AaArgs a = aa_args(h, (!odd && !h->cur_is_next) ? 1 : 0);
+    if (h->time_bulk && (h->iter % h->time_bulk) == 0) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, h->stream);
+        CU(h, launch_aa_bulk(odd, a, h->stream));
+        cudaEventRecord(e1, h->stream);
+        h->bulk_events.push_back(e0);
+        h->bulk_events.push_back(e1);
+        h->bulk_timed_launches += 1;
+        h->bulk_timed_cells += (long long)(a.x_end - a.x_begin) * (L.ny - (a.skip_rows ? 2 : 0));
+    } else {
+        CU(h, launch_aa_bulk(odd, a, h->stream));
+    }
+    if (!odd) {
+        CU(h, launch_aa_fix_even(a, h->bc, h->d_ring, h->n_ring, h->d_solids, h->n_solid, h->stream));
+        h->launches += 2;
+        if (h->periodic_x) { CU(h, launch_wrap(h->f[0], L, 1, 0, h->stream)); h->launches += 1; }
+        if (h->periodic_y) { CU(h, launch_wrap(h->f[0], L, 0, 1, h->stream)); h->launches += 1; }
+    } else {
+        // Constant fill last: in a periodic direction the reverse wrap also carries what solid
+        // cells pushed across the edge, and the fill must overwrite that.
+        const bool wrap = h->periodic_x || h->periodic_y;
+        CU(h, launch_aa_fix_odd(a, h->bc, h->d_ring, h->n_ring, h->d_fills, wrap ? 0 : h->n_fill, h->d_ring_out,
+                                h->periodic_x ? 1 : 0, h->periodic_y ? 1 : 0, h->stream));
+        h->launches += 2;
+        if (wrap) {
+            CU(h, launch_aa_unwrap(h->f[0], L, h->periodic_x ? 1 : 0, h->periodic_y ? 1 : 0, h->stream));
+            CU(h, launch_aa_fix_odd(a, h->bc, h->d_ring, 0, h->d_fills, h->n_fill, h->d_ring_out, 0, 0, h->stream));
+            h->launches += (h->periodic_x ? 1 : 0) + (h->periodic_y ? 1 : 0) + (h->n_fill ? 1 : 0);
+        }
+    }
+    h->aa_phase ^= 1;
+    h->prev_is_next = h->cur_is_next;
+    h->cur_is_next = true;
+    h->fresh = false;
+    h->macros_valid = false;
+    if (h->p.output_frequency > 0 && h->iter % h->p.output_frequency == 0) {
+        if ((int)h->pending.size() >= FORCE_SLOTS) {
+            int rc = drain_forces(h);
+            if (rc) return rc;
+        }
+        const int slot = (int)h->pending.size();
+        CU(h, launch_forces(h->f[0], aa_links(h), h->n_links, h->d_forces + 2 * slot, h->stream));
+        h->launches += 1;
+        h->pending.push_back({h->iter, slot});
+    }
+    h->iter += 1;
+    return LBM_OK;
+}
+
 // One reference iteration (include/LBMSolver.h:49-58) as kernel launches.
 int step_one(lbm_handle h) {
+    if (h->aa) return step_one_aa(h);
     const Layout& L = h->L;
     const bool pull = h->cur_is_next;
     double* dst = h->f[h->cur ^ 1];
@@ -369,7 +526,10 @@ int ensure_macros(lbm_handle h) {
     }
     if (h->snapshot_pending) CU(h, cudaStreamWaitEvent(h->stream, h->ev_snapshot, 0));
     if (h->west >= 0 || h->east >= 0) CU(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
-    CU(h, launch_macros(observe_args(h), h->d_rho, h->d_ux, h->d_uy, h->stream));
+    if (h->aa)
+        CU(h, launch_aa_macros(aa_observe(h), h->d_rho, h->d_ux, h->d_uy, h->stream));
+    else
+        CU(h, launch_macros(observe_args(h), h->d_rho, h->d_ux, h->d_uy, h->stream));
     h->launches += 1;
     h->macros_valid = true;
     return LBM_OK;
@@ -386,6 +546,11 @@ int ensure_scratch(lbm_handle h) {
 // kernels would only see one launch later: a store-less pass of the same kernels.
 int check_pending(lbm_handle h) {
     if (!h->cur_is_next) return LBM_OK;
+    if (h->aa) {
+        CU(h, launch_aa_check(aa_observe(h), h->d_first_bad, h->iter - 1, h->stream));
+        h->launches += 1;
+        return LBM_OK;
+    }
     if (h->west >= 0 || h->east >= 0) CU(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
     StepArgs a = step_args(h, h->f[h->cur], h->f[h->cur ^ 1], h->iter - 1, 0);
     CU(h, launch_bulk(BULK_VEC2, true, a, h->stream, 0, h->L.lnx));
@@ -434,6 +599,11 @@ int create_common(const lbm_params* p, int device, int rank, int world, const vo
     h->world = world;
     h->periodic_x = (p->flags & LBM_FLAG_PERIODIC_X) != 0;
     h->periodic_y = (p->flags & LBM_FLAG_PERIODIC_Y) != 0;
+    h->aa = (p->flags & LBM_FLAG_AA) != 0;
+    if (h->aa && world > 1) {
+        delete h;
+        return fail(nullptr, LBM_ERR_INVALID, "LBM_FLAG_AA is a single-slab variant (the x-slab halo exchange is A-B only)");
+    }
     const int lnx = p->nx / world;
     h->L = Layout::make(lnx, p->ny, p->nx, rank * lnx);
     // include/LBMConfig.h:61-65
@@ -478,9 +648,16 @@ int create_common(const lbm_params* p, int device, int rank, int world, const vo
     CUC(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
     const size_t fbytes = (size_t)h->L.plane * Q * sizeof(double);
     CUC(cudaMalloc(&h->f[0], fbytes));
-    CUC(cudaMalloc(&h->f[1], fbytes));
     CUC(cudaMemsetAsync(h->f[0], 0, fbytes, h->stream));
-    CUC(cudaMemsetAsync(h->f[1], 0, fbytes, h->stream));
+    if (h->aa) {
+        h->f[1] = nullptr;  // the point of the variant: no second buffer
+        const size_t rbytes = (size_t)(2 * h->L.ny + 2 * h->L.lnx) * Q * sizeof(double);
+        CUC(cudaMalloc(&h->d_ring_out, rbytes));
+        CUC(cudaMemsetAsync(h->d_ring_out, 0, rbytes, h->stream));
+    } else {
+        CUC(cudaMalloc(&h->f[1], fbytes));
+        CUC(cudaMemsetAsync(h->f[1], 0, fbytes, h->stream));
+    }
     h->h_mask.assign((size_t)h->L.cells_padded(), 0);
     CUC(cudaMalloc(&h->d_mask, h->h_mask.size()));
     CUC(cudaMemsetAsync(h->d_mask, 0, h->h_mask.size(), h->stream));
@@ -573,6 +750,7 @@ int lbm_destroy(lbm_handle h) {
     cudaFree(h->d_links); cudaFree(h->d_rho); cudaFree(h->d_ux); cudaFree(h->d_uy); cudaFree(h->d_scratch);
     cudaFree(h->d_first_bad); cudaFree(h->d_forces); cudaFree(h->d_maxbits);
     cudaFree(h->d_red); cudaFree(h->d_gather); cudaFree(h->d_first_bad_all);
+    cudaFree(h->d_fills); cudaFree(h->d_links_rev); cudaFree(h->d_links_nat); cudaFree(h->d_ring_out);
     if (h->ev_macros) cudaEventDestroy(h->ev_macros);
     if (h->ev_snapshot) cudaEventDestroy(h->ev_snapshot);
     if (h->ev_edge) cudaEventDestroy(h->ev_edge);
@@ -622,8 +800,13 @@ int lbm_initialise(lbm_handle h, double inlet_u) {
     const int wz = (!h->periodic_x && h->rank == 0) ? 1 : 0;
     const int ez = (!h->periodic_x && h->rank == h->world - 1) ? 1 : 0;
     const int sw = (h->p.flags & LBM_FLAG_SHEAR_WAVE_INIT) ? 1 : 0;
-    CU(h, launch_init(h->f[0], h->f[1], h->L, h->d_mask, h->bc, wz, ez, sw, inlet_u, h->stream));
+    CU(h, launch_init(h->f[0], h->aa ? h->f[0] : h->f[1], h->L, h->d_mask, h->bc, wz, ez, sw, inlet_u, h->stream));
     h->launches += 1;
+    if (h->aa) {
+        CU(h, launch_aa_ghosts(h->f[0], h->L, h->bc, wz, ez, h->stream));
+        h->launches += 1;
+        h->aa_phase = 0;
+    }
     const int big = INT_MAX;
     CU(h, cudaMemcpyAsync(h->d_first_bad, &big, sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
@@ -716,7 +899,10 @@ int lbm_get_forces(lbm_handle h, double* fx, double* fy) {
     int rc = drain_forces(h);
     if (rc) return rc;
     if (h->west >= 0 || h->east >= 0) CU(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
-    CU(h, launch_forces(h->f[h->cur], h->d_links, h->n_links, h->d_forces, h->stream));
+    if (h->aa)
+        CU(h, launch_forces(h->f[0], aa_links(h), h->n_links, h->d_forces, h->stream));
+    else
+        CU(h, launch_forces(h->f[h->cur], h->d_links, h->n_links, h->d_forces, h->stream));
     h->launches += 1;
     double v[2];
     CU(h, cudaMemcpyAsync(v, h->d_forces, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
@@ -762,7 +948,10 @@ int lbm_download_f(lbm_handle h, int which, double* aos) {
     int rc = ensure_scratch(h);
     if (rc) return rc;
     if (h->west >= 0 || h->east >= 0) CU(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
-    CU(h, launch_export_f(observe_args(h), which, h->d_scratch, h->stream));
+    if (h->aa)
+        CU(h, launch_aa_export(aa_observe(h), which, h->d_scratch, h->stream));
+    else
+        CU(h, launch_export_f(observe_args(h), which, h->d_scratch, h->stream));
     h->launches += 1;
     const size_t n = (size_t)(h->L.lnx + 2) * (h->L.ny + 2) * Q * sizeof(double);
     CU(h, cudaMemcpyAsync(aos, h->d_scratch, n, cudaMemcpyDeviceToHost, h->stream));
@@ -806,8 +995,13 @@ int lbm_upload_f(lbm_handle h, const double* aos, int iteration) {
     CU(h, launch_import_f(h->d_scratch, h->f[0], h->L, h->stream));
     const int wz = (!h->periodic_x && h->rank == 0) ? 1 : 0;
     const int ez = (!h->periodic_x && h->rank == h->world - 1) ? 1 : 0;
-    CU(h, launch_reset_ghosts(h->f[0], h->L, h->bc, wz, ez, h->stream));
-    CU(h, launch_reset_ghosts(h->f[1], h->L, h->bc, wz, ez, h->stream));
+    if (h->aa) {
+        CU(h, launch_aa_ghosts(h->f[0], h->L, h->bc, wz, ez, h->stream));
+        h->aa_phase = 0;
+    } else {
+        CU(h, launch_reset_ghosts(h->f[0], h->L, h->bc, wz, ez, h->stream));
+        CU(h, launch_reset_ghosts(h->f[1], h->L, h->bc, wz, ez, h->stream));
+    }
     h->launches += 3;
     const int big = INT_MAX;
     CU(h, cudaMemcpyAsync(h->d_first_bad, &big, sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -1009,8 +1203,8 @@ int lbm_set_params(lbm_handle h, const lbm_params* p) {
     if (!p) return fail(h, LBM_ERR_INVALID, "null params");
     if (p->nx != h->p.nx || p->ny != h->p.ny) return fail(h, LBM_ERR_INVALID, "nx / ny are fixed at creation");
     if (!(p->tau > 0.5)) return fail(h, LBM_ERR_INVALID, "tau must exceed 0.5");
-    if (((p->flags ^ h->p.flags) & (LBM_FLAG_PERIODIC_X | LBM_FLAG_PERIODIC_Y)) != 0)
-        return fail(h, LBM_ERR_INVALID, "periodicity is fixed at creation");
+    if (((p->flags ^ h->p.flags) & (LBM_FLAG_PERIODIC_X | LBM_FLAG_PERIODIC_Y | LBM_FLAG_AA)) != 0)
+        return fail(h, LBM_ERR_INVALID, "periodicity and the buffer scheme are fixed at creation");
     h->p = *p;
     h->cyl_x = static_cast<int>(p->cylinder_x * p->nx);
     h->cyl_y = static_cast<int>(p->cylinder_y * p->ny);

@@ -81,4 +81,49 @@ cudaError_t launch_import_f(const double* aos, double* f, const Layout& L, cudaS
 cudaError_t launch_reset_ghosts(double* f, const Layout& L, const BcArgs& b, int west_zero, int east_zero,
                                 cudaStream_t s);
 
+// ---- in-place AA variant (lbm_aa.cu) ------------------------------------------------------------
+struct AaArgs {
+    double* f;  // the single population buffer
+    Layout L;
+    double tau_inv, Fx, Fy;
+    int forced;
+    int* first_bad;
+    int bad_iter;
+    int first;      // E-step on a fresh f_current (after initialise / upload): no boundary rule, no check
+    int skip_rows;  // walls: rows 0 and ny-1 are ring cells, left to the fix-up kernel
+    int x_begin, x_end;  // bulk columns (inlet / outlet columns are ring cells too)
+    int variant;
+};
+// A slot [x][i] of a fluid cell whose upstream neighbour x - c_i is a solid or a non-periodic
+// ghost: nobody pushes into it, the O-step fix-up writes the constant (0: w_i, 1: 0.0, 2: e_i).
+struct AaFill {
+    long long off;
+    int kind, i;
+};
+struct AaObserve {
+    const double* f;
+    Layout L;
+    const unsigned char* mask;
+    BcArgs bc;
+    int phase;        // 0: natural layout (after initialise / upload / an O-step), 1: reversed (after an E-step)
+    int cur_is_next;  // at least one iteration done since initialise / upload
+    int fresh;
+    const double* ring_out;  // post-collision populations of the ring cells after an O-step
+    int periodic_x, periodic_y;
+    int west_zero, east_zero;
+    int shear_wave;
+    double u0;
+    double tau_inv, Fx, Fy;
+};
+cudaError_t launch_aa_bulk(bool odd, const AaArgs& a, cudaStream_t s);
+cudaError_t launch_aa_fix_even(const AaArgs& a, const BcArgs& b, const int2* ring, int n_ring, const int2* solids,
+                               int n_solid, cudaStream_t s);
+cudaError_t launch_aa_fix_odd(const AaArgs& a, const BcArgs& b, const int2* ring, int n_ring, const AaFill* fills,
+                              int n_fill, double* ring_out, int open_x, int open_y, cudaStream_t s);
+cudaError_t launch_aa_unwrap(double* f, const Layout& L, int do_x, int do_y, cudaStream_t s);
+cudaError_t launch_aa_ghosts(double* f, const Layout& L, const BcArgs& b, int west_zero, int east_zero, cudaStream_t s);
+cudaError_t launch_aa_macros(const AaObserve& o, double* rho, double* ux, double* uy, cudaStream_t s);
+cudaError_t launch_aa_export(const AaObserve& o, int which, double* aos, cudaStream_t s);
+cudaError_t launch_aa_check(const AaObserve& o, int* first_bad, int bad_iter, cudaStream_t s);
+
 }  // namespace lbm

@@ -48,7 +48,9 @@ enum {
     LBM_FLAG_PERIODIC_X = 1,  /* wrap in x instead of Zou-He inlet/outlet            */
     LBM_FLAG_PERIODIC_Y = 2,  /* wrap in y instead of the wall reflection             */
     LBM_FLAG_NO_CYLINDER = 4, /* obstacle-free domain                                 */
-    LBM_FLAG_SHEAR_WAVE_INIT = 8 /* u = (inlet_velocity*sin(2*pi*y/ny), 0) initial field */
+    LBM_FLAG_SHEAR_WAVE_INIT = 8, /* u = (inlet_velocity*sin(2*pi*y/ny), 0) initial field */
+    LBM_FLAG_AA = 16 /* in-place AA-pattern variant: ONE population buffer instead of the A-B pair
+                        (same populations bit for bit; rho/ux/uy equal to rounding).  Single slab. */
 };
 
 /* Mirrors LBM::SimulationParams (include/LBMConfig.h:36-52) field for field, then extensions. */
