@@ -19,7 +19,7 @@ namespace {
 void usage() {
     std::cout << "lbm_solver [--nx N] [--ny N] [--steps N] [--of N] [--tau X] [--uin X] [--cx X] [--cy X] [--cr X]\n"
                  "           [--vtk 0|1] [--vtk-start N] [--sync-vtk] [--periodic-x] [--periodic-y] [--no-cylinder]\n"
-                 "           [--shear-wave] [--fx X] [--fy X] [--no-final]\n";
+                 "           [--shear-wave] [--aa] [--fx X] [--fy X] [--no-final]\n";
 }
 }  // namespace
 
@@ -45,6 +45,7 @@ int main(int argc, char* argv[]) {
         else if (k == "--periodic-y") params.flags |= LBM_FLAG_PERIODIC_Y;
         else if (k == "--no-cylinder") params.flags |= LBM_FLAG_NO_CYLINDER;
         else if (k == "--shear-wave") params.flags |= LBM_FLAG_SHEAR_WAVE_INIT;
+        else if (k == "--aa") params.flags |= LBM_FLAG_AA;
         else if (k == "--fx") params.body_force_x = std::atof(val());
         else if (k == "--fy") params.body_force_y = std::atof(val());
         else if (k == "--no-final") final_results = false;
