@@ -19,13 +19,15 @@ namespace {
 void usage() {
     std::cout << "lbm_solver [--nx N] [--ny N] [--steps N] [--of N] [--tau X] [--uin X] [--cx X] [--cy X] [--cr X]\n"
                  "           [--vtk 0|1] [--vtk-start N] [--sync-vtk] [--periodic-x] [--periodic-y] [--no-cylinder]\n"
-                 "           [--shear-wave] [--aa] [--fx X] [--fy X] [--no-final]\n";
+                 "           [--shear-wave] [--aa] [--fx X] [--fy X] [--no-final]\n"
+                 "           [--checkpoint FILE] [--restart FILE]\n";
 }
 }  // namespace
 
 int main(int argc, char* argv[]) {
     LBM::SimulationParams params;
     bool vtk = true, final_results = true;
+    std::string checkpoint_out, restart_from;
     for (int a = 1; a < argc; ++a) {
         const std::string k = argv[a];
         auto val = [&]() -> const char* { return a + 1 < argc ? argv[++a] : "0"; };
@@ -49,6 +51,8 @@ int main(int argc, char* argv[]) {
         else if (k == "--fx") params.body_force_x = std::atof(val());
         else if (k == "--fy") params.body_force_y = std::atof(val());
         else if (k == "--no-final") final_results = false;
+        else if (k == "--checkpoint") checkpoint_out = val();
+        else if (k == "--restart") restart_from = val();
         else {
             usage();
             return k == "--help" || k == "-h" ? 0 : 2;
@@ -61,6 +65,7 @@ int main(int argc, char* argv[]) {
         const bool root = solver.get_grid().mpi_rank() == 0;
 
         solver.initialise();
+        if (!restart_from.empty()) solver.load_checkpoint(restart_from);
         const auto t0 = std::chrono::steady_clock::now();
         const bool success = solver.run(io_manager);
         const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -73,6 +78,7 @@ int main(int argc, char* argv[]) {
             std::cout << "run(): " << seconds << " s, "
                       << (double)params.nx * params.ny * params.num_timesteps / seconds / 1e6 << " MLUPS (wall clock, output included)"
                       << std::endl;
+        if (!checkpoint_out.empty()) solver.save_checkpoint(checkpoint_out);
         if (final_results) io_manager.write_final_results(solver.get_grid(), solver.get_params());
         if (root) std::cout << "\nSimulation completed successfully!" << std::endl;
     } catch (const std::exception& e) {

@@ -13,6 +13,7 @@
 // Errors surface as std::runtime_error carrying lbm_last_error(), which src/main.cpp:29 catches.
 #pragma once
 
+#include <cstdint>
 #include <cstdio>
 #include <stdexcept>
 #include <string>
@@ -148,6 +149,38 @@ class Grid {
         invalidate();
         return unstable_at;
     }
+    // ---- checkpoint / restart (extension; the reference keeps its state in RAM only) ----
+    // One file per slab: a 64-byte header and the padded AoS f_current (reference layout,
+    // include/LBMGrid.h:105-107) of this slab.  Restarting from it continues the run bit for bit.
+    void save_checkpoint(const std::string& path) const {
+        lbm_info now;
+        check(lbm_get_info(h_, &now));
+        const std::vector<double>& f = fetch(LBM_F_CURRENT);
+        std::FILE* fp = std::fopen(slab_file(path).c_str(), "wb");
+        if (!fp) throw std::runtime_error("lbm_b200: cannot write " + slab_file(path));
+        const int64_t head[8] = {0x4c424d3230304231LL, info_.global_nx, info_.global_ny, info_.local_nx, info_.x_start,
+                                 now.iteration, world_, (int64_t)f.size()};
+        const bool ok = std::fwrite(head, sizeof(head), 1, fp) == 1 && std::fwrite(f.data(), sizeof(double), f.size(), fp) == f.size();
+        std::fclose(fp);
+        if (!ok) throw std::runtime_error("lbm_b200: short write to " + slab_file(path));
+    }
+    // Returns the iteration the next step will execute.
+    int load_checkpoint(const std::string& path) {
+        std::FILE* fp = std::fopen(slab_file(path).c_str(), "rb");
+        if (!fp) throw std::runtime_error("lbm_b200: cannot read " + slab_file(path));
+        int64_t head[8];
+        std::vector<double> f((size_t)total_nx() * total_ny() * Q);
+        const bool ok = std::fread(head, sizeof(head), 1, fp) == 1 && head[0] == 0x4c424d3230304231LL &&
+                        head[1] == info_.global_nx && head[2] == info_.global_ny && head[3] == info_.local_nx &&
+                        head[4] == info_.x_start && head[6] == world_ && head[7] == (int64_t)f.size() &&
+                        std::fread(f.data(), sizeof(double), f.size(), fp) == f.size();
+        std::fclose(fp);
+        if (!ok) throw std::runtime_error("lbm_b200: " + slab_file(path) + " does not match this grid / slab layout");
+        check(lbm_upload_f(h_, f.data(), (int)head[5]));
+        invalidate();
+        return (int)head[5];
+    }
+
     void check(int rc) const {
         if (rc != LBM_OK) throw std::runtime_error(std::string("lbm_b200: ") + lbm_last_error(h_));
     }
@@ -163,6 +196,9 @@ class Grid {
         if (rc != LBM_OK) throw std::runtime_error(std::string("lbm_b200: ") + lbm_last_error(nullptr));
     }
     void refresh_info() { check(lbm_get_info(h_, &info_)); }
+    std::string slab_file(const std::string& path) const {
+        return world_ == 1 ? path : path + ".slab" + std::to_string(rank_) + "of" + std::to_string(world_);
+    }
     size_t f_index(int x, int y, int i) const { return ((size_t)y * total_nx() + x) * Q + i; }  // reference :105-107
     size_t m_index(int x, int y) const { return (size_t)y * local_nx() + x; }                   // reference :109-111
 

@@ -52,7 +52,7 @@ class Solver {
         std::unique_ptr<FrameWriter> frames;
         if (enable_vtk_output_ && params_.async_vtk) frames = std::make_unique<FrameWriter>(grid_);
 
-        int t = 0;
+        int t = first_timestep_;
         while (t < T) {
             // this chunk runs iterations t .. last, where last is the next output step (or T-1)
             const int next_out = ((t + of - 1) / of) * of;
@@ -83,6 +83,10 @@ class Solver {
         return true;
     }
 
+    // Extensions: checkpoint after run() / restart before run() (state = f_current + timestep).
+    void save_checkpoint(const std::string& path) const { grid_.save_checkpoint(path); }
+    void load_checkpoint(const std::string& path) { first_timestep_ = grid_.load_checkpoint(path); }
+
     const Grid& get_grid() const { return grid_; }
     const SimulationParams& get_params() const { return params_; }
 
@@ -107,6 +111,7 @@ class Solver {
     SimulationParams params_;
     Grid grid_;
     bool enable_vtk_output_;
+    int first_timestep_ = 0;  // > 0 after load_checkpoint: run() continues at that iteration
 };
 
 }  // namespace LBM

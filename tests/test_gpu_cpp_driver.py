@@ -120,3 +120,22 @@ def test_driver_two_slabs(exe, tmp_path):
     assert np.array_equal(vf[:, 2], np.array(["%.8f" % v for v in o.ux.ravel()], dtype=float))
     assert np.array_equal(vf[:, 5], np.array(["%.8f" % v for v in mag.ravel()], dtype=float))
     assert "Simulation completed successfully!" in out
+
+
+def test_checkpoint_restart_continues_bit_for_bit(exe, tmp_path):
+    """300 iterations in one go == 160 iterations, checkpoint, a NEW process restarts and runs to 300:
+    same forces.csv rows from the restart on, same final fields (extension)."""
+    a, b = tmp_path / "straight", tmp_path / "split"
+    a.mkdir()
+    b.mkdir()
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    base = [exe, "--nx", "256", "--ny", "64", "--of", "20", "--cr", "0.1", "--uin", "0.05", "--vtk", "0"]
+    subprocess.run(base + ["--steps", "300"], cwd=a, check=True, capture_output=True, env=env)
+    subprocess.run(base + ["--steps", "160", "--checkpoint", "state.ckpt", "--no-final"], cwd=b, check=True, capture_output=True, env=env)
+    first = open(b / "forces.csv").read()
+    subprocess.run(base + ["--steps", "300", "--restart", "state.ckpt"], cwd=b, check=True, capture_output=True, env=env)
+    second = open(b / "forces.csv").read()
+    straight = open(a / "forces.csv").read().splitlines()
+    assert first.splitlines() == straight[:1 + 8]            # header + t = 0..140
+    assert second.splitlines() == straight[:1] + straight[9:]  # header + t = 160..280
+    assert open(a / "velocity_field.csv").read() == open(b / "velocity_field.csv").read()
