@@ -28,6 +28,7 @@
 
 #include "lbm_cell.cuh"
 #include "lbm_kernels.cuh"
+#include "lbm_launch.cuh"
 
 namespace lbm {
 
@@ -73,6 +74,8 @@ __device__ __forceinline__ int ring_slot(int x, int y, const Layout& L) {
 // `wa` / `wb`: may the first / second cell of the pair be written (false on a wall row).
 template <bool FIRST>
 __global__ void __launch_bounds__(128) k_aa_even_vec2(AaArgs a) {
+    pdl_wait();
+    pdl_release();
     const Layout& L = a.L;
     const int y = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
     if (y >= L.ny) return;
@@ -105,6 +108,8 @@ __global__ void __launch_bounds__(128) k_aa_even_vec2(AaArgs a) {
 }
 
 __global__ void __launch_bounds__(128) k_aa_odd_vec2(AaArgs a) {
+    pdl_wait();
+    pdl_release();
     const Layout& L = a.L;
     const int y = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
     if (y >= L.ny) return;
@@ -145,6 +150,8 @@ __global__ void __launch_bounds__(128) k_aa_odd_vec2(AaArgs a) {
 // One cell per thread: any ny.
 template <bool ODD, bool FIRST>
 __global__ void __launch_bounds__(256) k_aa_scalar(AaArgs a) {
+    pdl_wait();
+    pdl_release();
     const Layout& L = a.L;
     const int y = blockIdx.x * blockDim.x + threadIdx.x;
     if (y >= L.ny) return;
@@ -174,6 +181,8 @@ __global__ void __launch_bounds__(256) k_aa_scalar(AaArgs a) {
 // reset of every solid cell to w.
 __global__ void __launch_bounds__(128) k_aa_fix_even(AaArgs a, BcArgs b, const int2* __restrict__ ring, int n_ring,
                                                      const int2* __restrict__ solids, int n_solid) {
+    pdl_wait();
+    pdl_release();
     const Layout& L = a.L;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < n_ring) {
@@ -203,6 +212,8 @@ __global__ void __launch_bounds__(128) k_aa_fix_even(AaArgs a, BcArgs b, const i
 __global__ void __launch_bounds__(128) k_aa_fix_odd(AaArgs a, BcArgs b, const int2* __restrict__ ring, int n_ring,
                                                     const AaFill* __restrict__ fills, int n_fill,
                                                     double* __restrict__ ring_out, int open_x, int open_y) {
+    pdl_wait();
+    pdl_release();
     const Layout& L = a.L;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < n_ring) {
@@ -232,6 +243,8 @@ __global__ void __launch_bounds__(128) k_aa_fix_odd(AaArgs a, BcArgs b, const in
 // Reverse wrap after an O-step in a periodic direction: what was pushed into a ghost line belongs
 // to the interior line at the opposite edge.
 __global__ void k_aa_unwrap(double* __restrict__ f, Layout L, int do_x, int do_y, int rows_open) {
+    pdl_wait();
+    pdl_release();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (do_x) {
         const int y = t - 1;  // -1 .. ny when the rows are open (periodic y), else 0 .. ny-1
@@ -470,40 +483,40 @@ cudaError_t launch_aa_bulk(bool odd, const AaArgs& a, cudaStream_t s) {
     const int ncols = a.x_end - a.x_begin;
     if (ncols <= 0) return cudaSuccess;
     const int gy = ncols < 65535 ? ncols : 65535;
+    cudaError_t e = cudaSuccess;
     if (a.L.ny % 2 == 0 && a.variant != BULK_SCALAR) {
         dim3 grid(cdiv(a.L.ny / 2, 128), gy);
-        if (odd) k_aa_odd_vec2<<<grid, 128, 0, s>>>(a);
-        else if (a.first) k_aa_even_vec2<true><<<grid, 128, 0, s>>>(a);
-        else k_aa_even_vec2<false><<<grid, 128, 0, s>>>(a);
+        if (odd) e = launch_chain(k_aa_odd_vec2, grid, dim3(128), s, a);
+        else if (a.first) e = launch_chain(k_aa_even_vec2<true>, grid, dim3(128), s, a);
+        else e = launch_chain(k_aa_even_vec2<false>, grid, dim3(128), s, a);
     } else {
         dim3 grid(cdiv(a.L.ny, 256), gy);
-        if (odd) k_aa_scalar<true, false><<<grid, 256, 0, s>>>(a);
-        else if (a.first) k_aa_scalar<false, true><<<grid, 256, 0, s>>>(a);
-        else k_aa_scalar<false, false><<<grid, 256, 0, s>>>(a);
+        if (odd) e = launch_chain(k_aa_scalar<true, false>, grid, dim3(256), s, a);
+        else if (a.first) e = launch_chain(k_aa_scalar<false, true>, grid, dim3(256), s, a);
+        else e = launch_chain(k_aa_scalar<false, false>, grid, dim3(256), s, a);
     }
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_aa_fix_even(const AaArgs& a, const BcArgs& b, const int2* ring, int n_ring, const int2* solids,
                                int n_solid, cudaStream_t s) {
     const long long n = (long long)n_ring + n_solid;
     if (n == 0) return cudaSuccess;
-    k_aa_fix_even<<<cdiv(n, 128), 128, 0, s>>>(a, b, ring, n_ring, solids, n_solid);
-    return cudaGetLastError();
+    return launch_chain(k_aa_fix_even, dim3(cdiv(n, 128)), dim3(128), s, a, b, ring, n_ring, solids, n_solid);
 }
 
 cudaError_t launch_aa_fix_odd(const AaArgs& a, const BcArgs& b, const int2* ring, int n_ring, const AaFill* fills,
                               int n_fill, double* ring_out, int open_x, int open_y, cudaStream_t s) {
     const long long n = (long long)n_ring + n_fill;
     if (n == 0) return cudaSuccess;
-    k_aa_fix_odd<<<cdiv(n, 128), 128, 0, s>>>(a, b, ring, n_ring, fills, n_fill, ring_out, open_x, open_y);
-    return cudaGetLastError();
+    return launch_chain(k_aa_fix_odd, dim3(cdiv(n, 128)), dim3(128), s, a, b, ring, n_ring, fills, n_fill, ring_out, open_x, open_y);
 }
 
 cudaError_t launch_aa_unwrap(double* f, const Layout& L, int do_x, int do_y, cudaStream_t s) {
-    if (do_x) k_aa_unwrap<<<cdiv(L.ny + 2, 256), 256, 0, s>>>(f, L, 1, 0, do_y);
-    if (do_y) k_aa_unwrap<<<cdiv(L.lnx + 2, 256), 256, 0, s>>>(f, L, 0, 1, 0);
-    return cudaGetLastError();
+    cudaError_t e = cudaSuccess;
+    if (do_x) e = launch_chain(k_aa_unwrap, dim3(cdiv(L.ny + 2, 256)), dim3(256), s, f, L, 1, 0, do_y);
+    if (do_y && e == cudaSuccess) e = launch_chain(k_aa_unwrap, dim3(cdiv(L.lnx + 2, 256)), dim3(256), s, f, L, 0, 1, 0);
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_aa_ghosts(double* f, const Layout& L, const BcArgs& b, int west_zero, int east_zero, cudaStream_t s) {

@@ -13,6 +13,7 @@
 
 #include "lbm_cell.cuh"
 #include "lbm_kernels.cuh"
+#include "lbm_launch.cuh"
 
 namespace lbm {
 
@@ -65,6 +66,8 @@ __device__ __forceinline__ void apply_bc(double f[Q], int x, int y, const Layout
 // variants are measured against.
 template <bool PULL, bool FORCED>
 __global__ void __launch_bounds__(256) k_bulk_scalar(StepArgs a, int x_begin, int x_end) {
+    pdl_wait();
+    pdl_release();
     const Layout& L = a.L;
     const int y = blockIdx.x * blockDim.x + threadIdx.x;
     if (y >= L.ny) return;
@@ -85,6 +88,8 @@ __global__ void __launch_bounds__(256) k_bulk_scalar(StepArgs a, int x_begin, in
 // first one brought into L1).  Requires even ny.
 template <bool PULL, bool FORCED>
 __global__ void __launch_bounds__(128) k_bulk_vec2(StepArgs a, int x_begin, int x_end) {
+    pdl_wait();
+    pdl_release();
     const Layout& L = a.L;
     const int y = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
     if (y >= L.ny) return;
@@ -120,6 +125,8 @@ __global__ void __launch_bounds__(128) k_bulk_vec2(StepArgs a, int x_begin, int 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_fixup(StepArgs a, BcArgs b, int pull, const int2* __restrict__ ring,
                                                int n_ring, const int2* __restrict__ solids, int n_solid) {
+    pdl_wait();
+    pdl_release();
     const Layout& L = a.L;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < n_ring) {
@@ -149,6 +156,8 @@ __global__ void __launch_bounds__(128) k_fixup(StepArgs a, BcArgs b, int pull, c
 // them, are checked, collided and stored.  Runs on the communication stream ahead of the halo
 // exchange while the bulk kernel works on the interior columns (lbm_engine.cu: step_one).
 __global__ void __launch_bounds__(128) k_edge(StepArgs a, BcArgs b, const unsigned char* __restrict__ mask, int pull) {
+    pdl_wait();
+    pdl_release();
     const Layout& L = a.L;
     const int y = blockIdx.x * blockDim.x + threadIdx.x;
     if (y >= L.ny) return;
@@ -185,6 +194,8 @@ constexpr int FORCE_CHUNK = 2048;
 
 __global__ void __launch_bounds__(256) k_forces(const double* __restrict__ f, const Link* __restrict__ links,
                                                 int n_links, double* __restrict__ out) {
+    pdl_wait();
+    pdl_release();
     __shared__ double tx[FORCE_CHUNK], ty[FORCE_CHUNK];
     double acc = 0.0;  // thread 0: Fx, thread 32: Fy
     for (int base = 0; base < n_links; base += FORCE_CHUNK) {
@@ -210,6 +221,8 @@ __global__ void __launch_bounds__(256) k_forces(const double* __restrict__ f, co
 // ------------------------------------------------------------------------------------------
 // Periodic extensions: copy the opposite interior edge into the ghost ring.
 __global__ void k_wrap(double* __restrict__ f, Layout L, int wrap_x, int wrap_y) {
+    pdl_wait();
+    pdl_release();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y;
     double* p = f + i * L.plane;
@@ -453,26 +466,27 @@ cudaError_t launch_bulk(int variant, bool pull, const StepArgs& a, cudaStream_t 
         cudaError_t e = launch_bulk_tma(pull, a, s, x_begin, x_end);
         if (e != cudaErrorNotSupported) return e;  // shape not handled by the TMA kernel: fall through
     }
+    cudaError_t e = cudaSuccess;
     if (variant != BULK_SCALAR && (a.L.ny % 2 == 0)) {
         dim3 grid(cdiv(a.L.ny / 2, 128), ncols < 65535 ? ncols : 65535);
         if (pull) {
-            if (a.forced) k_bulk_vec2<true, true><<<grid, 128, 0, s>>>(a, x_begin, x_end);
-            else k_bulk_vec2<true, false><<<grid, 128, 0, s>>>(a, x_begin, x_end);
+            if (a.forced) e = launch_chain(k_bulk_vec2<true, true>, grid, dim3(128), s, a, x_begin, x_end);
+            else e = launch_chain(k_bulk_vec2<true, false>, grid, dim3(128), s, a, x_begin, x_end);
         } else {
-            if (a.forced) k_bulk_vec2<false, true><<<grid, 128, 0, s>>>(a, x_begin, x_end);
-            else k_bulk_vec2<false, false><<<grid, 128, 0, s>>>(a, x_begin, x_end);
+            if (a.forced) e = launch_chain(k_bulk_vec2<false, true>, grid, dim3(128), s, a, x_begin, x_end);
+            else e = launch_chain(k_bulk_vec2<false, false>, grid, dim3(128), s, a, x_begin, x_end);
         }
     } else {
         dim3 grid(cdiv(a.L.ny, 256), ncols < 65535 ? ncols : 65535);
         if (pull) {
-            if (a.forced) k_bulk_scalar<true, true><<<grid, 256, 0, s>>>(a, x_begin, x_end);
-            else k_bulk_scalar<true, false><<<grid, 256, 0, s>>>(a, x_begin, x_end);
+            if (a.forced) e = launch_chain(k_bulk_scalar<true, true>, grid, dim3(256), s, a, x_begin, x_end);
+            else e = launch_chain(k_bulk_scalar<true, false>, grid, dim3(256), s, a, x_begin, x_end);
         } else {
-            if (a.forced) k_bulk_scalar<false, true><<<grid, 256, 0, s>>>(a, x_begin, x_end);
-            else k_bulk_scalar<false, false><<<grid, 256, 0, s>>>(a, x_begin, x_end);
+            if (a.forced) e = launch_chain(k_bulk_scalar<false, true>, grid, dim3(256), s, a, x_begin, x_end);
+            else e = launch_chain(k_bulk_scalar<false, false>, grid, dim3(256), s, a, x_begin, x_end);
         }
     }
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_fixup(bool pull, const StepArgs& a, const BcArgs& b, const int2* ring, int n_ring,
@@ -480,29 +494,27 @@ cudaError_t launch_fixup(bool pull, const StepArgs& a, const BcArgs& b, const in
     if (!pull) n_ring = 0;  // the first iteration collides f_current as it is: no boundary pass before it
     const long long n = (long long)n_ring + n_solid;
     if (n == 0) return cudaSuccess;
-    k_fixup<<<cdiv(n, 128), 128, 0, s>>>(a, b, pull ? 1 : 0, ring, n_ring, solids, n_solid);
-    return cudaGetLastError();
+    return launch_chain(k_fixup, dim3(cdiv(n, 128)), dim3(128), s, a, b, pull ? 1 : 0, ring, n_ring, solids, n_solid);
 }
 
 cudaError_t launch_edge(bool pull, const StepArgs& a, const BcArgs& b, const unsigned char* mask, cudaStream_t s) {
     dim3 grid(cdiv(a.L.ny, 128), a.L.lnx > 1 ? 2 : 1);
-    k_edge<<<grid, 128, 0, s>>>(a, b, mask, pull ? 1 : 0);
-    return cudaGetLastError();
+    return launch_chain(k_edge, grid, dim3(128), s, a, b, mask, pull ? 1 : 0);
 }
 
 cudaError_t launch_forces(const double* f_next, const Link* links, int n_links, double* out, cudaStream_t s) {
-    k_forces<<<1, 256, 0, s>>>(f_next, links, n_links, out);
-    return cudaGetLastError();
+    return launch_chain(k_forces, dim3(1), dim3(256), s, f_next, links, n_links, out);
 }
 
 cudaError_t launch_wrap(double* f, const Layout& L, int wrap_x, int wrap_y, cudaStream_t s) {
+    cudaError_t e = cudaSuccess;
     if (wrap_x) {
-        k_wrap<<<dim3(cdiv(L.ny, 256), Q), 256, 0, s>>>(f, L, 1, 0);
+        e = launch_chain(k_wrap, dim3(cdiv(L.ny, 256), Q), dim3(256), s, f, L, 1, 0);
     }
     if (wrap_y) {
-        k_wrap<<<dim3(cdiv(L.lnx + 2, 256), Q), 256, 0, s>>>(f, L, 0, 1);
+        e = launch_chain(k_wrap, dim3(cdiv(L.lnx + 2, 256), Q), dim3(256), s, f, L, 0, 1);
     }
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_init(double* f0, double* f1, const Layout& L, const unsigned char* mask, const BcArgs& b,

@@ -1,7 +1,3 @@
-python -m pytest tests/test_gpu_aa.py -m gpu -x -q > gpurun_out/pytest_aa.log 2>&1; echo rc=$?; tail -5 gpurun_out/pytest_aa.log | cut -c1-300
-for w in slab c4; do python bench.py --workload $w --aa --no-cpu-baseline > gpurun_out/bench_aa_$w.json 2> gpurun_out/bench_aa_$w.err; python - <<PY
-import json
-j=json.load(open("gpurun_out/bench_aa_$w.json"))
-print("$w AA value", round(j["value"],1), "ms/step", round(j["ms_per_step"],5), "bulk frac", round(j["roofline"]["frac"],4), "e2e", round(j["e2e"]["value"],1), j["stable"])
-PY
-tail -2 gpurun_out/bench_aa_$w.err; done
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo rc=$?; tail -4 gpurun_out/pytest_gpu.log | cut -c1-300
+for pdl in 1 0; do for cfg in "c1" "c1 --aa" "c3" "slab"; do LBM_B200_PDL=$pdl python bench.py --workload $cfg --no-cpu-baseline --no-e2e --steps 2000 2>/dev/null | python -c "
+import json,sys; j=json.loads(sys.stdin.read()); print('pdl=$pdl $cfg', round(j['value'],1), 'ms/step', round(j['ms_per_step'],5), 'bulk ms', round(j['roofline']['avg_launch_ms'],5), 'whole', round(j['roofline_whole_step_frac'],4))"; done; done
