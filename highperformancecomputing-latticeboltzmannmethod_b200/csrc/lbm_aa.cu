@@ -71,17 +71,34 @@ __device__ __forceinline__ int ring_slot(int x, int y, const Layout& L) {
 
 // ------------------------------------------------------------------------------------------
 // Bulk kernels: every interior cell that is not a ring cell.  Two y-adjacent cells per thread.
-// `wa` / `wb`: may the first / second cell of the pair be written (false on a wall row).
-template <bool FIRST>
-__global__ void __launch_bounds__(128) k_aa_even_vec2(AaArgs a) {
+// A pair is "plain" when neither cell lies on a wall row or in the obstacle: those take the
+// unpredicated path; the few other pairs write cell by cell.  Solid cells are checked (the
+// reference's stability check sees what the fluid pushed into them) but never written or pushed
+// from; pairs deep inside the obstacle are skipped.
+template <bool FORCED>
+__device__ __forceinline__ void collide_pair(double fa[Q], double fb[Q], const AaArgs& a) {
+    const Moments ma = moments(fa), mb = moments(fb);
+    if (FORCED) {
+        bgk_forced(fa, ma, a.tau_inv, a.Fx, a.Fy, fa);
+        bgk_forced(fb, mb, a.tau_inv, a.Fx, a.Fy, fb);
+    } else {
+        bgk(fa, ma, a.tau_inv, fa);
+        bgk(fb, mb, a.tau_inv, fb);
+    }
+}
+
+template <bool FIRST, bool FORCED>
+__global__ void __launch_bounds__(128, 6) k_aa_even_vec2(AaArgs a) {
     pdl_wait();
     pdl_release();
     const Layout& L = a.L;
     const int y = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
     if (y >= L.ny) return;
-    const bool wa = !(a.skip_rows && y == 0), wb = !(a.skip_rows && y + 1 == L.ny - 1);
+    const bool wall_a = a.skip_rows && y == 0, wall_b = a.skip_rows && y + 1 == L.ny - 1;
     bool bad = false;
     for (int x = a.x_begin + blockIdx.y; x < a.x_end; x += gridDim.y) {
+        const int4 iv = column_run(a, x);
+        if (y >= iv.z && y + 1 < iv.w) continue;
         double* p = a.f + L.at(x + 1, y);
         double fa[Q], fb[Q];
 #pragma unroll
@@ -90,9 +107,9 @@ __global__ void __launch_bounds__(128) k_aa_even_vec2(AaArgs a) {
             fa[i] = v.x;
             fb[i] = v.y;
         }
-        if (!FIRST) bad |= (wa && any_bad(fa)) | (wb && any_bad(fb));
-        collide(fa, a);
-        collide(fb, a);
+        if (!FIRST) bad |= (!wall_a && any_bad(fa)) | (!wall_b && any_bad(fb));
+        collide_pair<FORCED>(fa, fb, a);
+        const bool wa = !wall_a && !(y >= iv.x && y < iv.y), wb = !wall_b && !(y + 1 >= iv.x && y + 1 < iv.y);
         if (wa && wb) {
 #pragma unroll
             for (int i = 0; i < Q; ++i) *reinterpret_cast<double2*>(p + oppi(i) * L.plane) = make_double2(fa[i], fb[i]);
@@ -107,16 +124,19 @@ __global__ void __launch_bounds__(128) k_aa_even_vec2(AaArgs a) {
     if (bad) atomicMin(a.first_bad, a.bad_iter);
 }
 
-__global__ void __launch_bounds__(128) k_aa_odd_vec2(AaArgs a) {
+template <bool FORCED>
+__global__ void __launch_bounds__(128, 6) k_aa_odd_vec2(AaArgs a) {
     pdl_wait();
     pdl_release();
     const Layout& L = a.L;
     const int y = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
     if (y >= L.ny) return;
-    const bool wa = !(a.skip_rows && y == 0), wb = !(a.skip_rows && y + 1 == L.ny - 1);
+    const bool wall_a = a.skip_rows && y == 0, wall_b = a.skip_rows && y + 1 == L.ny - 1;
     bool bad = false;
     for (int x = a.x_begin + blockIdx.y; x < a.x_end; x += gridDim.y) {
         const int gx = x + 1;
+        const int4 iv = column_run(a, x);
+        if (y >= iv.z && y + 1 < iv.w) continue;
         double fa[Q], fb[Q];
 #pragma unroll
         for (int i = 0; i < Q; ++i) {
@@ -130,15 +150,24 @@ __global__ void __launch_bounds__(128) k_aa_odd_vec2(AaArgs a) {
                 fb[i] = p[1];
             }
         }
-        bad |= (wa && any_bad(fa)) | (wb && any_bad(fb));
-        collide(fa, a);
-        collide(fb, a);
+        bad |= (!wall_a && any_bad(fa)) | (!wall_b && any_bad(fb));
+        collide_pair<FORCED>(fa, fb, a);
+        const bool wa = !wall_a && !(y >= iv.x && y < iv.y), wb = !wall_b && !(y + 1 >= iv.x && y + 1 < iv.y);
+        if (wa && wb) {
 #pragma unroll
-        for (int i = 0; i < Q; ++i) {
-            double* p = a.f + i * L.plane + L.at(gx + cxi(i), y + cyi(i));
-            if (cyi(i) == 0 && wa && wb) {
-                *reinterpret_cast<double2*>(p) = make_double2(fa[i], fb[i]);
-            } else {
+            for (int i = 0; i < Q; ++i) {
+                double* p = a.f + i * L.plane + L.at(gx + cxi(i), y + cyi(i));
+                if (cyi(i) == 0) {
+                    *reinterpret_cast<double2*>(p) = make_double2(fa[i], fb[i]);
+                } else {
+                    p[0] = fa[i];
+                    p[1] = fb[i];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < Q; ++i) {
+                double* p = a.f + i * L.plane + L.at(gx + cxi(i), y + cyi(i));
                 if (wa) p[0] = fa[i];
                 if (wb) p[1] = fb[i];
             }
@@ -159,11 +188,15 @@ __global__ void __launch_bounds__(256) k_aa_scalar(AaArgs a) {
     bool bad = false;
     for (int x = a.x_begin + blockIdx.y; x < a.x_end; x += gridDim.y) {
         const int gx = x + 1;
+        const int4 iv = column_run(a, x);
+        if (y >= iv.z && y < iv.w) continue;
+        const bool solid = (y >= iv.x && y < iv.y);
         double f[Q];
 #pragma unroll
         for (int i = 0; i < Q; ++i)
             f[i] = ODD ? a.f[oppi(i) * L.plane + L.at(gx - cxi(i), y - cyi(i))] : a.f[i * L.plane + L.at(gx, y)];
         if (!FIRST) bad |= any_bad(f);
+        if (solid) continue;
         collide(f, a);
 #pragma unroll
         for (int i = 0; i < Q; ++i) {
@@ -486,9 +519,9 @@ cudaError_t launch_aa_bulk(bool odd, const AaArgs& a, cudaStream_t s) {
     cudaError_t e = cudaSuccess;
     if (a.L.ny % 2 == 0 && a.variant != BULK_SCALAR) {
         dim3 grid(cdiv(a.L.ny / 2, 128), gy);
-        if (odd) e = launch_chain(k_aa_odd_vec2, grid, dim3(128), s, a);
-        else if (a.first) e = launch_chain(k_aa_even_vec2<true>, grid, dim3(128), s, a);
-        else e = launch_chain(k_aa_even_vec2<false>, grid, dim3(128), s, a);
+        if (odd) e = a.forced ? launch_chain(k_aa_odd_vec2<true>, grid, dim3(128), s, a) : launch_chain(k_aa_odd_vec2<false>, grid, dim3(128), s, a);
+        else if (a.first) e = a.forced ? launch_chain(k_aa_even_vec2<true, true>, grid, dim3(128), s, a) : launch_chain(k_aa_even_vec2<true, false>, grid, dim3(128), s, a);
+        else e = a.forced ? launch_chain(k_aa_even_vec2<false, true>, grid, dim3(128), s, a) : launch_chain(k_aa_even_vec2<false, false>, grid, dim3(128), s, a);
     } else {
         dim3 grid(cdiv(a.L.ny, 256), gy);
         if (odd) e = launch_chain(k_aa_scalar<true, false>, grid, dim3(256), s, a);

@@ -60,6 +60,16 @@ struct lbm_solver {
     int2* d_solids = nullptr;
     int n_solid = 0;
     int n_ring_edge = 0, n_solid_edge = 0;  // leading entries that lie in columns 0 / lnx-1
+    // Per-column solid runs (StepArgs::cols): where the solid cells of a column form one run the
+    // bulk kernels never store them, so they keep w without any reset.  The solid list is ordered
+    // [cells of columns without such a run][layer-1 cells: a non-solid neighbour][the rest]:
+    // the A-B fix-up resets only the first group every step, the AA fix-up the first two (fluid
+    // cells push into layer-1 cells in O-steps); the first iteration after initialise / upload
+    // resets every solid cell.
+    int4* d_cols = nullptr;
+    int col_lo = 0, col_hi = 0;  // columns whose table entry is not empty
+    int n_solid_loose = 0, n_solid_l1 = 0;
+    bool col_skip = true;
     Link* d_links = nullptr;
     int n_links = 0;
 
@@ -139,6 +149,9 @@ StepArgs step_args(lbm_handle h, const double* src, double* dst, int bad_iter, i
     a.first_bad = h->d_first_bad;
     a.bad_iter = bad_iter;
     a.write = write;
+    a.cols = h->d_cols;
+    a.col_lo = h->col_lo;
+    a.col_hi = h->col_hi;
     return a;
 }
 
@@ -172,6 +185,9 @@ AaArgs aa_args(lbm_handle h, int first) {
     a.x_begin = h->bc.inlet ? 1 : 0;
     a.x_end = h->bc.outlet ? h->L.lnx - 1 : h->L.lnx;
     a.variant = h->variant;
+    a.cols = h->d_cols;
+    a.col_lo = h->col_lo;
+    a.col_hi = h->col_hi;
     return a;
 }
 
@@ -248,7 +264,48 @@ int build_geometry(lbm_handle h) {
         return (int)(mid - v.begin());
     };
     h->n_ring_edge = edge_first(ring);
-    h->n_solid_edge = edge_first(solids);
+    std::vector<int4> cols((size_t)L.lnx, make_int4(0, 0, 0, 0));
+    {
+        auto deep = [&](int x, int y) -> bool {  // solid with eight solid neighbours
+            for (int i = 1; i < Q; ++i)
+                if (!h->h_mask[L.at(x + 1 - cxi(i), y - cyi(i))]) return false;
+            return true;
+        };
+        std::vector<char> loose_col((size_t)L.lnx, 0);
+        for (int x = 0; x < L.lnx; ++x) {
+            int ys = -1, ye = -1, n = 0, ds = -1, de = -1, nd = 0;
+            for (int y = 0; y < L.ny; ++y) {
+                if (!h->h_mask[L.at(x + 1, y)]) continue;
+                if (ys < 0) ys = y;
+                ye = y + 1;
+                ++n;
+                if (deep(x, y)) {
+                    if (ds < 0) ds = y;
+                    de = y + 1;
+                    ++nd;
+                }
+            }
+            if (n == 0) continue;
+            if (!h->col_skip || ye - ys != n) {  // several runs in this column: the list-driven reset handles it
+                loose_col[x] = 1;
+                continue;
+            }
+            cols[x] = (nd > 0 && de - ds == nd) ? make_int4(ys, ye, ds, de) : make_int4(ys, ye, 0, 0);
+        }
+        auto l1 = [&](const int2& c) { return !deep(c.x, c.y); };
+        auto m0 = std::stable_partition(solids.begin(), solids.end(), [&](const int2& c) { return loose_col[c.x] != 0; });
+        auto m1 = std::stable_partition(m0, solids.end(), l1);
+        h->n_solid_loose = (int)(m0 - solids.begin());
+        h->n_solid_l1 = (int)(m1 - m0);
+        h->col_lo = L.lnx;
+        h->col_hi = 0;
+        for (int x = 0; x < L.lnx; ++x)
+            if (cols[x].y > cols[x].x) {
+                h->col_lo = std::min(h->col_lo, x);
+                h->col_hi = std::max(h->col_hi, x + 1);
+            }
+        h->n_solid_edge = 0;  // edge-column solids need no separate treatment any more (k_edge goes by the mask)
+    }
     // links, in the reference's (y, x, i) order over solid cells
     for (int y = 0; y < L.ny; ++y)
         for (int x = -1; x <= L.lnx; ++x) {
@@ -300,6 +357,10 @@ int build_geometry(lbm_handle h) {
     cudaFree(h->d_fills); cudaFree(h->d_links_rev); cudaFree(h->d_links_nat);
     h->d_ring = nullptr; h->d_solids = nullptr; h->d_links = nullptr;
     h->d_fills = nullptr; h->d_links_rev = nullptr; h->d_links_nat = nullptr;
+    cudaFree(h->d_cols);
+    h->d_cols = nullptr;
+    CU(h, cudaMalloc(&h->d_cols, sizeof(int4) * cols.size()));
+    CU(h, cudaMemcpyAsync(h->d_cols, cols.data(), sizeof(int4) * cols.size(), cudaMemcpyHostToDevice, h->stream));
     if (h->aa && links_rev.size() != links.size())
         return fail(h, LBM_ERR_INVALID, "internal: link lists of the two buffer schemes disagree");
     h->n_fill = (int)fills.size();
@@ -367,6 +428,12 @@ int exchange(lbm_handle h, double* buf, cudaStream_t s) {
     return LBM_OK;
 }
 
+// Leading entries of the solid list that the per-step fix-up must reset to w (see lbm_solver).
+int solids_to_reset(lbm_handle h, bool steady, bool aa) {
+    if (!steady) return h->n_solid;  // first iteration after initialise / upload: an uploaded state may hold anything
+    return h->n_solid_loose + (aa ? h->n_solid_l1 : 0);
+}
+
 const Link* aa_links(lbm_handle h) {
     if (!h->cur_is_next) return h->d_links;  // fresh: f_next == f_current, natural addressing
     return h->aa_phase == 1 ? h->d_links_rev : h->d_links_nat;
@@ -393,7 +460,7 @@ int step_one_aa(lbm_handle h) {
         CU(h, launch_aa_bulk(odd, a, h->stream));
     }
     if (!odd) {
-        CU(h, launch_aa_fix_even(a, h->bc, h->d_ring, h->n_ring, h->d_solids, h->n_solid, h->stream));
+        CU(h, launch_aa_fix_even(a, h->bc, h->d_ring, h->n_ring, h->d_solids, solids_to_reset(h, !a.first, true), h->stream));
         h->launches += 2;
         if (h->periodic_x) { CU(h, launch_wrap(h->f[0], L, 1, 0, h->stream)); h->launches += 1; }
         if (h->periodic_y) { CU(h, launch_wrap(h->f[0], L, 0, 1, h->stream)); h->launches += 1; }
@@ -473,17 +540,26 @@ int step_one(lbm_handle h) {
         CU(h, cudaEventRecord(h->ev_comm, h->comm_stream));
         CU(h, bulk(1, L.lnx - 1));
         CU(h, launch_fixup(pull, a, h->bc, h->d_ring + h->n_ring_edge, h->n_ring - h->n_ring_edge,
-                           h->d_solids + h->n_solid_edge, h->n_solid - h->n_solid_edge, h->stream));
+                           h->d_solids + h->n_solid_edge, solids_to_reset(h, pull, false) - h->n_solid_edge, h->stream));
         h->launches += 3;
         edge_pending = true;
     } else {
         CU(h, bulk(0, L.lnx));
-        CU(h, launch_fixup(pull, a, h->bc, h->d_ring, h->n_ring, h->d_solids, h->n_solid, h->stream));
+        CU(h, launch_fixup(pull, a, h->bc, h->d_ring, h->n_ring, h->d_solids, solids_to_reset(h, pull, false), h->stream));
         h->launches += 2;
         if (multi) {
             int rc = exchange(h, dst, h->stream);
             if (rc) return rc;
         }
+    }
+    if (!pull && h->n_solid) {
+        // The buffer just read may hold anything in its solid cells (an uploaded f_current); it is the
+        // next destination and the bulk kernels never store solid cells: give them w once, now.
+        StepArgs back = a;
+        back.dst = h->f[h->cur];
+        if (split) CU(h, cudaStreamWaitEvent(h->stream, h->ev_edge, 0));  // the edge kernel reads that buffer too
+        CU(h, launch_fixup(false, back, h->bc, nullptr, 0, h->d_solids, h->n_solid, h->stream));
+        h->launches += 1;
     }
     if (h->periodic_x && h->world == 1) { CU(h, launch_wrap(dst, L, 1, 0, h->stream)); h->launches += 1; }
     if (h->periodic_y) {
@@ -619,6 +695,7 @@ int create_common(const lbm_params* p, int device, int rank, int world, const vo
     h->init_u = p->inlet_velocity;
     if (const char* v = std::getenv("LBM_B200_VARIANT")) h->variant = std::atoi(v);
     if (const char* v = std::getenv("LBM_B200_OVERLAP")) h->overlap = std::atoi(v) != 0;
+    if (const char* v = std::getenv("LBM_B200_COLSKIP")) h->col_skip = std::atoi(v) != 0;
     if (world > 1) {
         h->west = rank > 0 ? rank - 1 : (h->periodic_x ? world - 1 : -1);
         h->east = rank < world - 1 ? rank + 1 : (h->periodic_x ? 0 : -1);
@@ -750,7 +827,7 @@ int lbm_destroy(lbm_handle h) {
     cudaFree(h->d_links); cudaFree(h->d_rho); cudaFree(h->d_ux); cudaFree(h->d_uy); cudaFree(h->d_scratch);
     cudaFree(h->d_first_bad); cudaFree(h->d_forces); cudaFree(h->d_maxbits);
     cudaFree(h->d_red); cudaFree(h->d_gather); cudaFree(h->d_first_bad_all);
-    cudaFree(h->d_fills); cudaFree(h->d_links_rev); cudaFree(h->d_links_nat); cudaFree(h->d_ring_out);
+    cudaFree(h->d_cols); cudaFree(h->d_fills); cudaFree(h->d_links_rev); cudaFree(h->d_links_nat); cudaFree(h->d_ring_out);
     if (h->ev_macros) cudaEventDestroy(h->ev_macros);
     if (h->ev_snapshot) cudaEventDestroy(h->ev_snapshot);
     if (h->ev_edge) cudaEventDestroy(h->ev_edge);

@@ -73,11 +73,13 @@ __global__ void __launch_bounds__(256) k_bulk_scalar(StepArgs a, int x_begin, in
     if (y >= L.ny) return;
     bool bad = false;
     for (int x = x_begin + blockIdx.y; x < x_end; x += gridDim.y) {
+        const int4 iv = column_run(a, x);
+        if (y >= iv.z && y < iv.w) continue;  // deep inside the obstacle: stays w
         double f[Q];
         load_cell<PULL>(a.src, L, x + 1, y, f);
         if (PULL) bad |= any_unstable(f);
         collide_cell<FORCED>(f, a.tau_inv, a.Fx, a.Fy);
-        if (a.write) store_cell(a.dst, L, x + 1, y, f);
+        if (a.write && !(y >= iv.x && y < iv.y)) store_cell(a.dst, L, x + 1, y, f);
     }
     if (bad) atomicMin(a.first_bad, a.bad_iter);
 }
@@ -96,6 +98,9 @@ __global__ void __launch_bounds__(128) k_bulk_vec2(StepArgs a, int x_begin, int 
     bool bad = false;
     for (int x = x_begin + blockIdx.y; x < x_end; x += gridDim.y) {
         const int gx = x + 1;
+        const int4 iv = column_run(a, x);
+        if (y >= iv.z && y + 1 < iv.w) continue;  // both cells deep inside the obstacle: they stay w
+        const bool sa = (y >= iv.x && y < iv.y), sb = (y + 1 >= iv.x && y + 1 < iv.y);  // solid: never stored
         double fa[Q], fb[Q];
 #pragma unroll
         for (int i = 0; i < Q; ++i) {
@@ -114,9 +119,17 @@ __global__ void __launch_bounds__(128) k_bulk_vec2(StepArgs a, int x_begin, int 
         collide_cell<FORCED>(fa, a.tau_inv, a.Fx, a.Fy);
         collide_cell<FORCED>(fb, a.tau_inv, a.Fx, a.Fy);
         if (a.write) {
+            if (!sa && !sb) {
 #pragma unroll
-            for (int i = 0; i < Q; ++i)
-                *reinterpret_cast<double2*>(a.dst + i * L.plane + L.at(gx, y)) = make_double2(fa[i], fb[i]);
+                for (int i = 0; i < Q; ++i)
+                    *reinterpret_cast<double2*>(a.dst + i * L.plane + L.at(gx, y)) = make_double2(fa[i], fb[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < Q; ++i) {
+                    if (!sa) a.dst[i * L.plane + L.at(gx, y)] = fa[i];
+                    if (!sb) a.dst[i * L.plane + L.at(gx, y + 1)] = fb[i];
+                }
+            }
         }
     }
     if (bad) atomicMin(a.first_bad, a.bad_iter);

@@ -27,6 +27,12 @@ struct StepArgs {
     int* first_bad;  // device int, atomicMin'ed with bad_iter when an unstable value is seen
     int bad_iter;    // reference timestep whose check_stability these pulled values belong to
     int write;       // 0: check only, store nothing
+    // Per interior column x: rows [x, y) are solid and rows [z, w) are "deep" solid (all eight
+    // neighbours solid), when the solid cells of the column form one run; {0,0,0,0} otherwise.
+    // Solid cells are not stored (they keep w for ever), deep ones are skipped
+    // altogether.  nullptr: no table, every cell is processed and the fix-up resets the solids.
+    const int4* cols;
+    int col_lo, col_hi;  // only columns in [col_lo, col_hi) have a table entry worth loading
 };
 
 enum BulkVariant { BULK_SCALAR = 0, BULK_VEC2 = 1, BULK_TMA = 2 };
@@ -93,6 +99,8 @@ struct AaArgs {
     int skip_rows;  // walls: rows 0 and ny-1 are ring cells, left to the fix-up kernel
     int x_begin, x_end;  // bulk columns (inlet / outlet columns are ring cells too)
     int variant;
+    const int4* cols;  // as StepArgs::cols
+    int col_lo, col_hi;
 };
 // A slot [x][i] of a fluid cell whose upstream neighbour x - c_i is a solid or a non-periodic
 // ghost: nobody pushes into it, the O-step fix-up writes the constant (0: w_i, 1: 0.0, 2: e_i).
@@ -125,5 +133,14 @@ cudaError_t launch_aa_ghosts(double* f, const Layout& L, const BcArgs& b, int we
 cudaError_t launch_aa_macros(const AaObserve& o, double* rho, double* ux, double* uy, cudaStream_t s);
 cudaError_t launch_aa_export(const AaObserve& o, int which, double* aos, cudaStream_t s);
 cudaError_t launch_aa_check(const AaObserve& o, int* first_bad, int bad_iter, cudaStream_t s);
+
+// The solid run of column x, or an empty one (no load at all outside [col_lo, col_hi)).
+template <class Args>
+__device__ __forceinline__ int4 column_run(const Args& a, int x) {
+#if defined(__CUDA_ARCH__)
+    if (a.cols && x >= a.col_lo && x < a.col_hi) return __ldg(a.cols + x);
+#endif
+    return make_int4(0, 0, 0, 0);
+}
 
 }  // namespace lbm
