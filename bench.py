@@ -368,7 +368,7 @@ def main():
         bulk_ms = ms_bulk / bulk_launches
         achieved = (bulk_cells / bulk_launches) * BYTES_PER_UPDATE / (bulk_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic_per_launch(args.workload), "kernel": "k_bulk (fused pull collide-stream)",
+                "traffic": ncu_traffic_per_launch(args.workload + ("_aa" if args.aa else "")), "kernel": "k_bulk (fused pull collide-stream)",
                 "bytes_per_launch": (bulk_cells / bulk_launches) * BYTES_PER_UPDATE, "avg_launch_ms": bulk_ms,
                 "launches_timed": bulk_launches, "kernel_share_of_step": bulk_ms * args.steps / ms_total, "peak_source": peak_src,
                 "whole_step_frac": value * 1e6 * BYTES_PER_UPDATE / 1e9 / args.gpus / peak}

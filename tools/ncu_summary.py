@@ -20,6 +20,7 @@ from collections import OrderedDict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag, workload = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 else "slab")
+suffix = sys.argv[3] if len(sys.argv) > 3 else "bulk"  # gpurun_out/<tag>_<suffix>.ncu-rep
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 os.makedirs(P, exist_ok=True)
 
@@ -43,7 +44,7 @@ def short(name):
 
 # ---- launch list ------------------------------------------------------------------------------
 src = os.path.join(G, tag + "_launches.csv")
-if os.path.exists(src):
+if os.path.exists(src) and suffix == "bulk":
     shutil.copy(src, os.path.join(P, tag + "_launches.csv"))
     lines = [l for l in open(src) if l.startswith('"')]
     rows = list(csv.DictReader(io.StringIO("".join(lines))))
@@ -75,18 +76,21 @@ if os.path.exists(src):
     print(open(os.path.join(P, tag + "_launches_summary.md")).read())
 
 # ---- full capture -----------------------------------------------------------------------------
-rep = os.path.join(G, tag + "_bulk.ncu-rep")
+rep = os.path.join(G, tag + "_" + suffix + ".ncu-rep")
 if os.path.exists(rep):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     head, units, data = rows[0], rows[1], rows[2:]
+    all_data = data
     cols = [head.index(k) for k in KEEP if k in head]
-    with open(os.path.join(P, tag + "_bulk_raw.csv"), "w", newline="") as f:
+    with open(os.path.join(P, tag + "_" + suffix + "_raw.csv"), "w", newline="") as f:
         w = csv.writer(f)
         w.writerow(["kernel"] + [head[c] for c in cols])
         w.writerow(["unit"] + [units[c] for c in cols])
-        for d in data:
+        for d in all_data:
             w.writerow([short(d[head.index("Kernel Name")])] + [d[c] for c in cols])
+    # the traffic figure is that of the dominant (bulk collide-stream) kernel only
+    data = [d for d in all_data if re.search(r"k_bulk|k_aa_(odd|even)", d[head.index("Kernel Name")])]
 
     def col(name):
         c = head.index(name)
@@ -98,10 +102,10 @@ if os.path.exists(rep):
     tj = os.path.join(P, "bulk_traffic.json")
     j = json.load(open(tj)) if os.path.exists(tj) else {}
     j[workload] = {"dram_bytes_per_launch": per_launch, "dram_read": sum(rd) / len(rd), "dram_write": sum(wr) / len(wr),
-                   "launches_captured": len(rd), "kernel": short(data[0][head.index("Kernel Name")]),
-                   "source": "profiles/%s_bulk_raw.csv (ncu --set full --clock-control none)" % tag}
+                   "launches_captured": len(rd), "kernel": " / ".join(sorted({short(d[head.index("Kernel Name")]) for d in data})),
+                   "source": "profiles/%s_%s_raw.csv (ncu --set full --clock-control none)" % (tag, suffix)}
     json.dump(j, open(tj, "w"), indent=1)
     print(json.dumps(j[workload], indent=1))
     # stall reasons per source line (top 12 lines by samples)
     srcp = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda"], capture_output=True, text=True).stdout
-    open(os.path.join(P, tag + "_bulk_source.csv"), "w").write(srcp)
+    open(os.path.join(P, tag + "_" + suffix + "_source.csv"), "w").write(srcp)
