@@ -39,6 +39,12 @@ def main():
     out = os.path.join(ROOT, "tests", "golden", "re200_forces_reference.csv.gz")
     with gzip.GzipFile(out, "wb", mtime=0) as f:
         f.write(text.encode())
+    # final fields of the same run (ref_harness --dump), sampled every 16th cell, for a field-level check
+    import numpy as np
+
+    if os.path.exists(os.path.join(d, "rho.bin")):
+        samp = {k: np.fromfile(os.path.join(d, k + ".bin")).reshape(512, 2048)[::16, ::16].copy() for k in ("rho", "ux", "uy")}
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "re200_final_fields_sampled.npz"), stride=16, **samp)
     import strouhal
 
     tmp = os.path.join(d, "_forces_copy.csv")

@@ -153,3 +153,22 @@ def test_reference_main_cpp_compiles_unchanged_against_the_dropin_headers(built,
 def test_examples_driver_builds(built):
     subprocess.run(["make", "-C", os.path.join(ROOT, "examples")], check=True, capture_output=True)
     assert os.path.exists(os.path.join(ROOT, "examples", "lbm_solver"))
+
+
+def test_bootstrap_env_hands_the_nccl_id_to_every_rank(built, tmp_path):
+    """Two processes of one "launch": rank 0 creates the NCCL unique id, rank 1 receives the same
+    128 bytes through the id file (what a C++ driver started by torchrun --no-python relies on)."""
+    code = (
+        "import ctypes,sys;L=ctypes.CDLL(%r);r=ctypes.c_int();w=ctypes.c_int();l=ctypes.c_int();"
+        "b=ctypes.create_string_buffer(128);rc=L.lbm_bootstrap_env(ctypes.byref(r),ctypes.byref(w),ctypes.byref(l),b);"
+        "L.lbm_last_error.restype=ctypes.c_char_p;print(rc,r.value,w.value,b.raw.hex(),L.lbm_last_error(None).decode())" % LIB)
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    env.update(WORLD_SIZE="2", LBM_B200_ID_FILE=str(tmp_path / "nccl.id"))
+    procs = [subprocess.Popen(["python", "-c", code], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)), stdout=subprocess.PIPE, text=True)
+             for r in (1, 0)]  # rank 1 first: it has to wait for the file
+    outs = [p.communicate(timeout=120)[0].split(None, 4) for p in procs]
+    if any(o[0] == "-3" for o in outs):
+        pytest.skip("NCCL library not loadable here: " + outs[0][-1])
+    assert [o[0] for o in outs] == ["0", "0"], outs
+    assert outs[0][1:3] == ["1", "2"] and outs[1][1:3] == ["0", "2"]
+    assert outs[0][3] == outs[1][3] and len(outs[0][3]) == 256 and set(outs[0][3]) != {"0"}
