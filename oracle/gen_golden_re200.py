@@ -10,6 +10,9 @@ tools/strouhal.py (the headless scripts/lift.py) derives from it.
 
   python oracle/gen_golden_re200.py            # run the reference, then write the fixture
   python oracle/gen_golden_re200.py --from DIR # DIR already holds forces.csv of that run
+
+tests/golden/re200_forces_strict_prefix.csv.gz is the head of forces.csv of the same case run with
+oracle/_ref/lbm_ref_strict (OMP_NUM_THREADS=1; stopped after ~45 000 steps, complete rows kept).
 """
 import argparse
 import gzip
