@@ -22,7 +22,7 @@ FLAG_SHEAR_WAVE_INIT = 8
 FLAG_AA = 16
 
 F_CURRENT, F_NEXT = 0, 1
-VARIANT_SCALAR, VARIANT_VEC2, VARIANT_TMA = 0, 1, 2
+VARIANT_SCALAR, VARIANT_VEC2 = 0, 1
 
 
 class LbmError(RuntimeError):

@@ -1336,7 +1336,7 @@ int lbm_gather_macros(lbm_handle h, double* rho, double* ux, double* uy) {
 
 int lbm_set_kernel_variant(lbm_handle h, int variant) {
     CHECK_H(h);
-    if (variant < 0 || variant > 2) return fail(h, LBM_ERR_INVALID, "variant must be 0, 1 or 2");
+    if (variant < 0 || variant > 1) return fail(h, LBM_ERR_INVALID, "variant must be 0 or 1");
     h->variant = variant;
     return LBM_OK;
 }

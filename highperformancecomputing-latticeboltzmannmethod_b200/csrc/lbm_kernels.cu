@@ -1,5 +1,5 @@
-// lbm_kernels.cu -- sm_100a kernels of the D2Q9 collide-stream path (all but the TMA-pipelined bulk
-// kernel, which lives in lbm_bulk_tma.cu).  Compiled with -fmad=false: see lbm_cell.cuh.
+// lbm_kernels.cu -- sm_100a kernels of the D2Q9 collide-stream path, A-B double buffer (the in-place
+// AA variant lives in lbm_aa.cu).  Compiled with -fmad=false: see lbm_cell.cuh.
 //
 // Per iteration t >= 1 the engine launches, on one stream:
 //   k_bulk_*   every interior cell: new(c) = collide(pull(old))          branch-free, HBM-bound
@@ -469,16 +469,10 @@ inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
-cudaError_t launch_bulk_tma(bool pull, const StepArgs& a, cudaStream_t s, int x_begin, int x_end);  // lbm_bulk_tma.cu
-
 cudaError_t launch_bulk(int variant, bool pull, const StepArgs& a, cudaStream_t s, int x_begin, int x_end) {
     if (x_end < 0) x_end = a.L.lnx;
     const int ncols = x_end - x_begin;
     if (ncols <= 0) return cudaSuccess;
-    if (variant == BULK_TMA && pull && !a.forced && a.write) {
-        cudaError_t e = launch_bulk_tma(pull, a, s, x_begin, x_end);
-        if (e != cudaErrorNotSupported) return e;  // shape not handled by the TMA kernel: fall through
-    }
     cudaError_t e = cudaSuccess;
     if (variant != BULK_SCALAR && (a.L.ny % 2 == 0)) {
         dim3 grid(cdiv(a.L.ny / 2, 128), ncols < 65535 ? ncols : 65535);

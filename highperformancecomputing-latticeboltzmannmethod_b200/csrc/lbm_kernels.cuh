@@ -1,5 +1,5 @@
 // lbm_kernels.cuh -- launch interface of the sm_100a kernels (definitions in lbm_kernels.cu and
-// lbm_bulk_tma.cu).  Host code (lbm_engine.cu) sees only these plain functions.
+// lbm_aa.cu).  Host code (lbm_engine.cu) sees only these plain functions.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -35,7 +35,7 @@ struct StepArgs {
     int col_lo, col_hi;  // only columns in [col_lo, col_hi) have a table entry worth loading
 };
 
-enum BulkVariant { BULK_SCALAR = 0, BULK_VEC2 = 1, BULK_TMA = 2 };
+enum BulkVariant { BULK_SCALAR = 0, BULK_VEC2 = 1 };
 
 // Fused pull + collide over every interior cell, no boundary logic (reference
 // include/LBMSolver.h:84-145 minus the solid `continue`).  pull=false is the very first

@@ -53,7 +53,7 @@ def test_initial_state_matches_grid_initialise():
 
 
 @pytest.mark.parametrize("name", list(CASES))
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1])
 def test_steps_match_oracle(name, variant):
     case = CASES[name]
     s, o = make_solver(case, variant), O.Oracle(case)
@@ -138,7 +138,7 @@ def test_variants_are_bit_identical_to_each_other():
     case = CASES["256x64"]
     state = util.random_state(case, 7)
     outs = []
-    for v in (0, 1, 2):
+    for v in (0, 1):
         s = make_solver(case, v)
         s.upload_f(state, 0)
         s.step(25)
@@ -248,4 +248,21 @@ def test_full_size_slab_against_oracle():
     fx, fy = s.forces()
     ofx, ofy = o.forces()
     assert fx == ofx and fy == ofy  # 7904 links, reference summation order
+    s.close()
+
+
+@pytest.mark.parametrize("aa", [0, 16])
+@pytest.mark.parametrize("nx,ny", [(1, 1), (2, 2), (3, 1), (1, 5), (2, 3), (5, 2), (4, 7)])
+def test_degenerate_lattices(nx, ny, aa):
+    """Lattices where the inlet column is the outlet column, or the bottom wall row is the top one
+    (the reference applies both rules, in its serial order), down to one cell; 1 x 5 goes unstable
+    at the same timestep as the reference."""
+    case = O.Case(nx=nx, ny=ny, cylinder_radius=0.0, cylinder_x=0.9, cylinder_y=0.9, output_frequency=2)
+    s, o = make_solver(case, flags=aa), O.Oracle(case)
+    rows, bad = s.run(12)
+    want, obad = o.run(12)
+    assert bad == obad
+    assert np.array_equal(rows, want)
+    if bad == -1:
+        util.compare_state(s, o, "%dx%d aa=%d" % (nx, ny, aa), exact=True, macros_exact=(aa == 0))
     s.close()

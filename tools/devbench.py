@@ -30,7 +30,7 @@ def run(nx, ny, variant, steps=100, warm=10, flags=0, per_kernel=True):
 
 if __name__ == "__main__":
     sizes = [(2048, 512), (8192, 2048), (4096, 8192), (16384, 4096)]
-    variants = [int(v) for v in os.environ.get("VARIANTS", "0,1,2").split(",")]
+    variants = [int(v) for v in os.environ.get("VARIANTS", "0,1").split(",")]
     for nx, ny in sizes:
         for v in variants:
             try:
