@@ -139,3 +139,35 @@ def test_checkpoint_restart_continues_bit_for_bit(exe, tmp_path):
     assert first.splitlines() == straight[:1 + 8]            # header + t = 0..140
     assert second.splitlines() == straight[:1] + straight[9:]  # header + t = 160..280
     assert open(a / "velocity_field.csv").read() == open(b / "velocity_field.csv").read()
+
+
+@pytest.mark.parametrize("poke", [0, 1])
+def test_grid_accessors_follow_the_reference_conventions(tmp_path, poke):
+    """LBM::Grid's element accessors (ghost-inclusive f_current/f_next, interior rho/ux/uy/is_solid, the
+    getters, the writable f_current used for a caller-defined initial state) against the oracle."""
+    pkg = os.path.join(ROOT, "highperformancecomputing-latticeboltzmannmethod_b200")
+    exe = str(tmp_path / "grid_api_dump")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-mfma", "-pthread", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "grid_api_dump.cpp"), "-o", exe, "-L" + pkg, "-llbm_b200", "-Wl,-rpath," + pkg], check=True)
+    nx, ny, steps = 48, 20, 23
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run([exe, str(nx), str(ny), str(steps), str(poke), str(tmp_path)], cwd=tmp_path, capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    case = O.Case(nx=nx, ny=ny, output_frequency=5, cylinder_radius=0.15)
+    o = O.Oracle(case)
+    if poke:
+        o.f_current[4, 3, 1] *= 1.25
+        o.f_current[7, 10, 6] += 0.01
+        o.f_current[ny, nx, 8] *= 0.5
+    rows, bad = o.run(steps)
+    assert bad == -1
+    for k, shape in (("f_current", (ny + 2, nx + 2, 9)), ("f_next", (ny + 2, nx + 2, 9)), ("rho", (ny, nx)), ("ux", (ny, nx)), ("uy", (ny, nx))):
+        got = np.fromfile(tmp_path / (k + ".bin")).reshape(shape)
+        assert np.array_equal(got, getattr(o, k)), k
+    assert np.array_equal(np.fromfile(tmp_path / "solid.bin").reshape(ny, nx) != 0, o.solid != 0)
+    lines = r.stdout.splitlines()
+    g = [l for l in lines if l.startswith("getters")][0].split()[1:]
+    assert [int(v) for v in g] == [0, 0, nx, ny, nx + 2, ny + 2, nx, ny, 0, 1, 1, 1]
+    st = [l for l in lines if l.startswith("stable")][0].split()
+    assert st[1] == "1" and float(st[3]) == o.max_velocity() and st[5] == "1"
+    assert open(tmp_path / "forces.csv").read() == O.format_forces_csv(rows)
