@@ -446,7 +446,9 @@ def main():
             "config": {"workload": cfg["label"], "nx": cfg["nx"], "ny": cfg["ny"], "tau": cfg["tau"],
                        "inlet_velocity": cfg["inlet_velocity"], "output_frequency": cfg["output_frequency"],
                        "layout": "fp64 SoA, in-place AA pattern (one buffer)" if args.aa else "fp64 SoA, A-B double buffer", "kernel_variant": info.kernel_variant,
-                       "partition": "x-slab x%d, NCCL send/recv halo (3 populations per face)" % world if world > 1 else "single GPU",
+                       "partition": ("x-slab x%d, halo (3 populations per face) %s" % (
+                           world, "stored into the neighbour's ghost column by the edge kernel (CUDA IPC peer memory over NVLink)"
+                           if info.halo_p2p else "by NCCL send/recv")) if world > 1 else "single GPU",
                        "l2": "inputs_exceed_l2 (%.2f GB per population buffer)" % (info.bytes_per_buffer / 1e9)
                        if info.bytes_per_buffer > 200e6 else "L2-resident working set (not roofline evidence)"},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks,

@@ -55,7 +55,7 @@ class CInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "abi_version", "global_nx", "global_ny", "local_nx", "local_ny", "x_start", "y_start", "rank", "world",
         "device", "cyl_x", "cyl_y", "cyl_r", "solid_cells", "links", "iteration")] + [
-        ("bytes_per_buffer", C.c_int64), ("row_pitch", C.c_int32), ("kernel_variant", C.c_int32)]
+        ("bytes_per_buffer", C.c_int64), ("row_pitch", C.c_int32), ("kernel_variant", C.c_int32), ("halo_p2p", C.c_int32)]
 
 
 @dataclass

@@ -99,6 +99,14 @@ struct lbm_solver {
     bool overlap = true;
 
     ncclComm_t comm = nullptr;
+    // Fused edge + halo kernel over CUDA-IPC peer memory (k_edge_p2p); NCCL send/recv is the fallback.
+    bool p2p = false;
+    int* d_flags = nullptr;              // [0] from west, [1] from east: last exchange delivered by that neighbour
+    unsigned int* d_blocks_done = nullptr;
+    double* peer_f[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [side: 0 west, 1 east][buffer]
+    int* peer_flags[2] = {nullptr, nullptr};
+    void* ipc_opened[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    int edge_seq = 0;                    // exchanges issued so far (identical on every rank)
     double* d_red = nullptr;       // small device scratch for lbm_allreduce
     double* d_gather = nullptr;    // rank 0: one slab of rho/ux/uy received from a peer
     int* d_first_bad_all = nullptr;
@@ -404,6 +412,103 @@ int drain_forces(lbm_handle h) {
     return LBM_OK;
 }
 
+P2pArgs p2p_args(lbm_handle h, int dst_index, int seq) {
+    P2pArgs x;
+    x.peer_dst_west = h->west >= 0 ? h->peer_f[0][dst_index] : nullptr;
+    x.peer_dst_east = h->east >= 0 ? h->peer_f[1][dst_index] : nullptr;
+    x.my_flags = h->d_flags;
+    x.west_flag = h->west >= 0 ? h->peer_flags[0] + 1 : nullptr;  // I am my west neighbour's east side
+    x.east_flag = h->east >= 0 ? h->peer_flags[1] + 0 : nullptr;
+    x.blocks_done = h->d_blocks_done;
+    x.seq = seq;
+    return x;
+}
+
+// Everything in flight between the slabs has landed (peer stores of the neighbours' last edge
+// kernels, or the NCCL exchange): observers of ghost columns call this first.
+int join_halo(lbm_handle h) {
+    if (h->west < 0 && h->east < 0) return LBM_OK;
+    if (h->p2p) {
+        if (h->edge_seq > 0) CU(h, launch_wait_halo(p2p_args(h, 0, h->edge_seq), h->stream));
+    } else {
+        CU(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
+    }
+    return LBM_OK;
+}
+
+// All slabs have reached this point and their streams are drained (an NCCL all-reduce as a barrier).
+int slab_barrier(lbm_handle h) {
+    if (!h->comm) return LBM_OK;
+    CU(h, cudaStreamSynchronize(h->comm_stream));
+    NC(h, nccl_api().AllReduce(h->d_red, h->d_red, 1, ncclDouble, ncclSum, h->comm, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return LBM_OK;
+}
+
+// Exchange CUDA IPC handles of both population buffers and the flag words with the x-neighbours
+// and map theirs.  Any failure on any rank leaves every rank on the NCCL path.
+int setup_p2p(lbm_handle h) {
+    struct Pack { cudaIpcMemHandle_t f0, f1, flags; };
+    const NcclApi& N = nccl_api();
+    bool ok = true;
+    if (const char* v = std::getenv("LBM_B200_P2P")) ok = std::atoi(v) != 0;
+    Pack mine{};
+    if (cudaMalloc(&h->d_flags, 64 * sizeof(int)) != cudaSuccess || cudaMalloc(&h->d_blocks_done, sizeof(unsigned int)) != cudaSuccess)
+        return fail(h, LBM_ERR_NOMEM, "cudaMalloc of the halo flags failed");
+    CU(h, cudaMemsetAsync(h->d_flags, 0, 64 * sizeof(int), h->stream));
+    CU(h, cudaMemsetAsync(h->d_blocks_done, 0, sizeof(unsigned int), h->stream));
+    ok = ok && cudaIpcGetMemHandle(&mine.f0, h->f[0]) == cudaSuccess && cudaIpcGetMemHandle(&mine.f1, h->f[1]) == cudaSuccess &&
+         cudaIpcGetMemHandle(&mine.flags, h->d_flags) == cudaSuccess;
+    cudaGetLastError();
+    Pack* d_io = nullptr;  // [0] mine, [1] from west, [2] from east
+    CU(h, cudaMalloc(&d_io, 3 * sizeof(Pack)));
+    CU(h, cudaMemcpyAsync(d_io, &mine, sizeof(Pack), cudaMemcpyHostToDevice, h->stream));
+    NC(h, N.GroupStart());
+    if (h->east >= 0) {
+        NC(h, N.Send(d_io, sizeof(Pack), ncclChar, h->east, h->comm, h->stream));
+        NC(h, N.Recv(d_io + 2, sizeof(Pack), ncclChar, h->east, h->comm, h->stream));
+    }
+    if (h->west >= 0) {
+        NC(h, N.Send(d_io, sizeof(Pack), ncclChar, h->west, h->comm, h->stream));
+        NC(h, N.Recv(d_io + 1, sizeof(Pack), ncclChar, h->west, h->comm, h->stream));
+    }
+    NC(h, N.GroupEnd());
+    Pack got[3];
+    CU(h, cudaMemcpyAsync(got, d_io, 3 * sizeof(Pack), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    cudaFree(d_io);
+    for (int side = 0; side < 2 && ok; ++side) {
+        if ((side == 0 ? h->west : h->east) < 0) continue;
+        const Pack& p = got[1 + side];
+        const cudaIpcMemHandle_t* hs[3] = {&p.f0, &p.f1, &p.flags};
+        for (int k = 0; k < 3 && ok; ++k)
+            ok = cudaIpcOpenMemHandle(&h->ipc_opened[side][k], *hs[k], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+        if (ok) {
+            h->peer_f[side][0] = static_cast<double*>(h->ipc_opened[side][0]);
+            h->peer_f[side][1] = static_cast<double*>(h->ipc_opened[side][1]);
+            h->peer_flags[side] = static_cast<int*>(h->ipc_opened[side][2]);
+        }
+    }
+    cudaGetLastError();
+    double agree = ok ? 1.0 : 0.0;  // all or nothing
+    CU(h, cudaMemcpyAsync(h->d_red, &agree, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    NC(h, N.AllReduce(h->d_red, h->d_red, 1, ncclDouble, ncclMin, h->comm, h->stream));
+    CU(h, cudaMemcpyAsync(&agree, h->d_red, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->p2p = agree > 0.5;
+    return LBM_OK;
+}
+
+void close_p2p(lbm_handle h) {
+    for (int side = 0; side < 2; ++side)
+        for (int k = 0; k < 3; ++k)
+            if (h->ipc_opened[side][k]) {
+                cudaIpcCloseMemHandle(h->ipc_opened[side][k]);
+                h->ipc_opened[side][k] = nullptr;
+            }
+    cudaGetLastError();
+}
+
 // Halo exchange of the freshly written buffer: interior column lnx -> east neighbour's W ghost
 // (populations 1,5,8 move in +x), interior column 1 -> west neighbour's E ghost (3,6,7).
 // Rows 0..ny-1 only: ghost-row/corner entries keep the initial equilibrium as in the 1-rank
@@ -505,7 +610,6 @@ int step_one(lbm_handle h) {
     StepArgs a = step_args(h, h->f[h->cur], dst, h->iter - 1, 1);
     const bool multi = (h->west >= 0 || h->east >= 0);
     const bool split = multi && h->overlap && L.lnx >= 4;
-    bool edge_pending = false;  // this iteration's edge columns are still in flight on the comm stream
 
     auto bulk = [&](int x0, int x1) -> cudaError_t {
         if (h->time_bulk && (h->iter % h->time_bulk) == 0) {
@@ -524,25 +628,57 @@ int step_one(lbm_handle h) {
         return launch_bulk(h->variant, pull, a, h->stream, x0, x1);
     };
 
-    if (split) {
-        // Two streams, no stream waits for the wire:
-        //   comm stream : [wait: interior of t-1 done] edge columns of t -> halo exchange of t
-        //   main stream : [wait: edge columns of t-1 done] interior columns of t, interior fix-up
-        // Only the edge kernel reads ghost columns, and it runs behind the previous exchange on
-        // the same stream; the interior kernel needs columns 0 and lnx-1 of the previous buffer
-        // (written by the previous edge kernel) but never a ghost column.
-        CU(h, cudaStreamWaitEvent(h->stream, h->ev_edge, 0));
-        CU(h, cudaStreamWaitEvent(h->comm_stream, h->ev_main, 0));
-        CU(h, launch_edge(pull, a, h->bc, h->d_mask, h->comm_stream));
-        CU(h, cudaEventRecord(h->ev_edge, h->comm_stream));
-        int rc = exchange(h, dst, h->comm_stream);
-        if (rc) return rc;
-        CU(h, cudaEventRecord(h->ev_comm, h->comm_stream));
+    if (split && h->p2p) {
+        // Two launches, one stream, no NCCL call and no event -- the single-GPU chain.  The two slab-edge
+        // columns are the FIRST blocks of the bulk launch: they wait for the neighbours' previous push (it
+        // landed a whole kernel ago), compute, and store their face populations straight into the
+        // neighbours' ghost columns over NVLink while the interior blocks run (k_bulk_vec2_p2p).
+        // Odd ny / scalar variant: bulk over every column, then the same edge work inside the fix-up.
+        h->edge_seq += 1;
+        const P2pArgs px = p2p_args(h, h->cur ^ 1, h->edge_seq);
+        const bool fused = bulk_p2p_supported(h->variant, a);
+        if (!fused) {
+            CU(h, bulk(0, L.lnx));
+            CU(h, launch_fixup_p2p(pull, a, h->bc, h->d_ring + h->n_ring_edge, h->n_ring - h->n_ring_edge,
+                                   h->d_solids + h->n_solid_edge, solids_to_reset(h, pull, false) - h->n_solid_edge, h->d_mask,
+                                   px, h->stream));
+        } else {
+            if (h->time_bulk && (h->iter % h->time_bulk) == 0) {
+                cudaEvent_t e0, e1;
+                cudaEventCreate(&e0);
+                cudaEventCreate(&e1);
+                cudaEventRecord(e0, h->stream);
+                CU(h, launch_bulk_p2p(pull, a, h->bc, h->d_mask, px, h->stream));
+                cudaEventRecord(e1, h->stream);
+                h->bulk_events.push_back(e0);
+                h->bulk_events.push_back(e1);
+                h->bulk_timed_launches += 1;
+                h->bulk_timed_cells += (long long)L.lnx * L.ny;
+            } else {
+                CU(h, launch_bulk_p2p(pull, a, h->bc, h->d_mask, px, h->stream));
+            }
+            CU(h, launch_fixup(pull, a, h->bc, h->d_ring + h->n_ring_edge, h->n_ring - h->n_ring_edge,
+                               h->d_solids + h->n_solid_edge, solids_to_reset(h, pull, false) - h->n_solid_edge, h->stream));
+        }
+        h->launches += 2;
+    } else if (split) {
+        // The wire is never on the critical path, and the main stream stays one unbroken chain of
+        // dependent launches (bulk -> fix-up -> edge -> bulk ...):
+        //   main stream : interior columns of t, interior fix-up, [halo of t-1 landed?] edge columns of t
+        //   comm stream : [edge columns of t done] halo exchange of t
+        // Only the edge kernel reads ghost columns; it comes last, a whole interior kernel after the
+        // exchange it depends on was issued, so its wait is satisfied long before it is reached.
         CU(h, bulk(1, L.lnx - 1));
         CU(h, launch_fixup(pull, a, h->bc, h->d_ring + h->n_ring_edge, h->n_ring - h->n_ring_edge,
                            h->d_solids + h->n_solid_edge, solids_to_reset(h, pull, false) - h->n_solid_edge, h->stream));
+        CU(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
+        CU(h, launch_edge(pull, a, h->bc, h->d_mask, h->stream));
+        CU(h, cudaEventRecord(h->ev_edge, h->stream));
+        CU(h, cudaStreamWaitEvent(h->comm_stream, h->ev_edge, 0));
+        int rc = exchange(h, dst, h->comm_stream);
+        if (rc) return rc;
+        CU(h, cudaEventRecord(h->ev_comm, h->comm_stream));
         h->launches += 3;
-        edge_pending = true;
     } else {
         CU(h, bulk(0, L.lnx));
         CU(h, launch_fixup(pull, a, h->bc, h->d_ring, h->n_ring, h->d_solids, solids_to_reset(h, pull, false), h->stream));
@@ -557,14 +693,16 @@ int step_one(lbm_handle h) {
         // next destination and the bulk kernels never store solid cells: give them w once, now.
         StepArgs back = a;
         back.dst = h->f[h->cur];
-        if (split) CU(h, cudaStreamWaitEvent(h->stream, h->ev_edge, 0));  // the edge kernel reads that buffer too
         CU(h, launch_fixup(false, back, h->bc, nullptr, 0, h->d_solids, h->n_solid, h->stream));
         h->launches += 1;
     }
     if (h->periodic_x && h->world == 1) { CU(h, launch_wrap(dst, L, 1, 0, h->stream)); h->launches += 1; }
     if (h->periodic_y) {
         // ghost columns must be final before the rows (corners) are wrapped
-        if (split) CU(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
+        if (split) {
+            int rc = join_halo(h);
+            if (rc) return rc;
+        }
         CU(h, launch_wrap(dst, L, 0, 1, h->stream));
         h->launches += 1;
     }
@@ -576,13 +714,11 @@ int step_one(lbm_handle h) {
             if (rc) return rc;
         }
         const int slot = (int)h->pending.size();
-        if (edge_pending) CU(h, cudaStreamWaitEvent(h->stream, h->ev_edge, 0));  // links may end in an edge column
         CU(h, launch_forces(dst, h->d_links, h->n_links, h->d_forces + 2 * slot, h->stream));
         h->launches += 1;
         h->pending.push_back({h->iter, slot});
     }
 
-    if (split) CU(h, cudaEventRecord(h->ev_main, h->stream));
     h->cur ^= 1;
     h->prev_is_next = h->cur_is_next;
     h->cur_is_next = true;
@@ -601,7 +737,7 @@ int ensure_macros(lbm_handle h) {
         CU(h, cudaMalloc(&h->d_uy, n));
     }
     if (h->snapshot_pending) CU(h, cudaStreamWaitEvent(h->stream, h->ev_snapshot, 0));
-    if (h->west >= 0 || h->east >= 0) CU(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
+    { int rc_ = join_halo(h); if (rc_) return rc_; }
     if (h->aa)
         CU(h, launch_aa_macros(aa_observe(h), h->d_rho, h->d_ux, h->d_uy, h->stream));
     else
@@ -627,7 +763,7 @@ int check_pending(lbm_handle h) {
         h->launches += 1;
         return LBM_OK;
     }
-    if (h->west >= 0 || h->east >= 0) CU(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
+    { int rc_ = join_halo(h); if (rc_) return rc_; }
     StepArgs a = step_args(h, h->f[h->cur], h->f[h->cur ^ 1], h->iter - 1, 0);
     CU(h, launch_bulk(BULK_VEC2, true, a, h->stream, 0, h->L.lnx));
     CU(h, launch_fixup(true, a, h->bc, h->d_ring, h->n_ring, nullptr, 0, h->stream));
@@ -640,7 +776,7 @@ int check_pending(lbm_handle h) {
 int read_first_bad(lbm_handle h, int* out) {
     int v = INT_MAX;
     const int* src = h->d_first_bad;
-    if (h->west >= 0 || h->east >= 0) CU(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));  // edge kernels flag too
+    { int rc_ = join_halo(h); if (rc_) return rc_; }  // edge kernels flag too
     if (h->comm) {
         NC(h, nccl_api().AllReduce(h->d_first_bad, h->d_first_bad_all, 1, ncclInt, ncclMin, h->comm, h->stream));
         src = h->d_first_bad_all;
@@ -763,6 +899,13 @@ int create_common(const lbm_params* p, int device, int rank, int world, const vo
             std::remove(g_id_file.c_str());
             g_id_file.clear();
         }
+        if (h->west >= 0 || h->east >= 0) {
+            int rc = setup_p2p(h);
+            if (rc) {
+                std::string m = h->err;
+                return bail(rc, m);
+            }
+        }
     }
     // ring list etc. for an obstacle-free domain; lbm_setup_geometry adds the cylinder
     {
@@ -817,6 +960,8 @@ int lbm_destroy(lbm_handle h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+    if (h->comm && h->p2p) slab_barrier(h);  // no neighbour may still be storing into this slab's memory
+    close_p2p(h);
     if (h->comm) nccl_api().CommDestroy(h->comm);
     for (cudaEvent_t e : h->bulk_events) cudaEventDestroy(e);
     for (cudaEvent_t e : h->marks)
@@ -827,6 +972,7 @@ int lbm_destroy(lbm_handle h) {
     cudaFree(h->d_links); cudaFree(h->d_rho); cudaFree(h->d_ux); cudaFree(h->d_uy); cudaFree(h->d_scratch);
     cudaFree(h->d_first_bad); cudaFree(h->d_forces); cudaFree(h->d_maxbits);
     cudaFree(h->d_red); cudaFree(h->d_gather); cudaFree(h->d_first_bad_all);
+    cudaFree(h->d_flags); cudaFree(h->d_blocks_done);
     cudaFree(h->d_cols); cudaFree(h->d_fills); cudaFree(h->d_links_rev); cudaFree(h->d_links_nat); cudaFree(h->d_ring_out);
     if (h->ev_macros) cudaEventDestroy(h->ev_macros);
     if (h->ev_snapshot) cudaEventDestroy(h->ev_snapshot);
@@ -855,6 +1001,7 @@ int lbm_get_info(lbm_handle h, lbm_info* o) {
     o->bytes_per_buffer = (int64_t)h->L.plane * Q * (int64_t)sizeof(double);
     o->row_pitch = h->L.PY;
     o->kernel_variant = h->variant;
+    o->halo_p2p = h->p2p ? 1 : 0;
     return LBM_OK;
 }
 
@@ -872,6 +1019,10 @@ int lbm_initialise(lbm_handle h, double inlet_u) {
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaStreamSynchronize(h->comm_stream));  // nothing of an earlier run may still touch the buffers
     CU(h, cudaStreamSynchronize(h->stream));
+    if (h->p2p) {  // ... nor a neighbour's edge kernel (it stores into this slab's ghost columns)
+        int rc = slab_barrier(h);
+        if (rc) return rc;
+    }
     h->init_u = inlet_u;
     equilibrium_init(1.0, inlet_u, 0.0, h->bc.e);
     const int wz = (!h->periodic_x && h->rank == 0) ? 1 : 0;
@@ -896,6 +1047,7 @@ int lbm_initialise(lbm_handle h, double inlet_u) {
     h->macros_valid = false;
     h->pending.clear();
     h->force_log.clear();
+    if (h->p2p) return slab_barrier(h);  // every slab initialised before any neighbour pushes a halo into it
     return LBM_OK;
 }
 
@@ -975,7 +1127,7 @@ int lbm_get_forces(lbm_handle h, double* fx, double* fy) {
     CU(h, cudaSetDevice(h->device));
     int rc = drain_forces(h);
     if (rc) return rc;
-    if (h->west >= 0 || h->east >= 0) CU(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
+    { int rc_ = join_halo(h); if (rc_) return rc_; }
     if (h->aa)
         CU(h, launch_forces(h->f[0], aa_links(h), h->n_links, h->d_forces, h->stream));
     else
@@ -1024,7 +1176,7 @@ int lbm_download_f(lbm_handle h, int which, double* aos) {
     CU(h, cudaSetDevice(h->device));
     int rc = ensure_scratch(h);
     if (rc) return rc;
-    if (h->west >= 0 || h->east >= 0) CU(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
+    { int rc_ = join_halo(h); if (rc_) return rc_; }
     if (h->aa)
         CU(h, launch_aa_export(aa_observe(h), which, h->d_scratch, h->stream));
     else
@@ -1066,6 +1218,11 @@ int lbm_upload_f(lbm_handle h, const double* aos, int iteration) {
     rc = drain_forces(h);
     if (rc) return rc;
     CU(h, cudaStreamSynchronize(h->comm_stream));
+    if (h->p2p) {
+        CU(h, cudaStreamSynchronize(h->stream));
+        int rc2 = slab_barrier(h);
+        if (rc2) return rc2;
+    }
     const size_t n = (size_t)(h->L.lnx + 2) * (h->L.ny + 2) * Q * sizeof(double);
     CU(h, cudaMemcpyAsync(h->d_scratch, aos, n, cudaMemcpyHostToDevice, h->stream));
     h->cur = 0;
@@ -1089,6 +1246,7 @@ int lbm_upload_f(lbm_handle h, const double* aos, int iteration) {
     h->initialised = true;
     h->iter = iteration;
     h->macros_valid = false;
+    if (h->p2p) return slab_barrier(h);
     return LBM_OK;
 }
 
@@ -1166,7 +1324,7 @@ int lbm_time_steps(lbm_handle h, int n_steps, int per_kernel, float* ms_total, f
     int rc = lbm_step(h, n_steps);
     h->time_bulk = 0;
     if (rc) return rc;
-    if (h->west >= 0 || h->east >= 0) CU(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
+    { int rc_ = join_halo(h); if (rc_) return rc_; }
     CU(h, cudaEventRecord(e1, h->stream));
     CU(h, cudaEventSynchronize(e1));
     float ms = 0.f;
@@ -1202,7 +1360,7 @@ int lbm_event_record(lbm_handle h, int slot) {
     CU(h, cudaSetDevice(h->device));
     if (!h->marks[slot]) CU(h, cudaEventCreate(&h->marks[slot]));
     // everything the handle has in flight on its side streams is ordered before the mark
-    if (h->west >= 0 || h->east >= 0) CU(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
+    { int rc_ = join_halo(h); if (rc_) return rc_; }
     if (h->snapshot_pending) CU(h, cudaStreamWaitEvent(h->stream, h->ev_snapshot, 0));
     CU(h, cudaEventRecord(h->marks[slot], h->stream));
     return LBM_OK;

@@ -89,49 +89,53 @@ __global__ void __launch_bounds__(256) k_bulk_scalar(StepArgs a, int x_begin, in
 // misaligned by one element and use two 64-bit loads each (the second one hits the lines the
 // first one brought into L1).  Requires even ny.
 template <bool PULL, bool FORCED>
-__global__ void __launch_bounds__(128) k_bulk_vec2(StepArgs a, int x_begin, int x_end) {
-    pdl_wait();
-    pdl_release();
+__device__ __forceinline__ bool bulk_vec2_column(const StepArgs& a, int x, int y) {
     const Layout& L = a.L;
-    const int y = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
-    if (y >= L.ny) return;
-    bool bad = false;
-    for (int x = x_begin + blockIdx.y; x < x_end; x += gridDim.y) {
-        const int gx = x + 1;
-        const int4 iv = column_run(a, x);
-        if (y >= iv.z && y + 1 < iv.w) continue;  // both cells deep inside the obstacle: they stay w
-        const bool sa = (y >= iv.x && y < iv.y), sb = (y + 1 >= iv.x && y + 1 < iv.y);  // solid: never stored
-        double fa[Q], fb[Q];
+    const int gx = x + 1;
+    const int4 iv = column_run(a, x);
+    if (y >= iv.z && y + 1 < iv.w) return false;  // both cells deep inside the obstacle: they stay w
+    const bool sa = (y >= iv.x && y < iv.y), sb = (y + 1 >= iv.x && y + 1 < iv.y);  // solid: never stored
+    double fa[Q], fb[Q];
 #pragma unroll
-        for (int i = 0; i < Q; ++i) {
-            const int dx = PULL ? cxi(i) : 0, dy = PULL ? cyi(i) : 0;
-            const double* p = a.src + i * L.plane + L.at(gx - dx, y - dy);
-            if (dy == 0) {
-                const double2 v = __ldg(reinterpret_cast<const double2*>(p));
-                fa[i] = v.x;
-                fb[i] = v.y;
-            } else {
-                fa[i] = __ldg(p);
-                fb[i] = __ldg(p + 1);
-            }
+    for (int i = 0; i < Q; ++i) {
+        const int dx = PULL ? cxi(i) : 0, dy = PULL ? cyi(i) : 0;
+        const double* p = a.src + i * L.plane + L.at(gx - dx, y - dy);
+        if (dy == 0) {
+            const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+            fa[i] = v.x;
+            fb[i] = v.y;
+        } else {
+            fa[i] = __ldg(p);
+            fb[i] = __ldg(p + 1);
         }
-        if (PULL) bad |= any_unstable(fa) | any_unstable(fb);
-        collide_cell<FORCED>(fa, a.tau_inv, a.Fx, a.Fy);
-        collide_cell<FORCED>(fb, a.tau_inv, a.Fx, a.Fy);
-        if (a.write) {
-            if (!sa && !sb) {
+    }
+    const bool bad = PULL ? (any_unstable(fa) | any_unstable(fb)) : false;
+    collide_cell<FORCED>(fa, a.tau_inv, a.Fx, a.Fy);
+    collide_cell<FORCED>(fb, a.tau_inv, a.Fx, a.Fy);
+    if (a.write) {
+        if (!sa && !sb) {
 #pragma unroll
-                for (int i = 0; i < Q; ++i)
-                    *reinterpret_cast<double2*>(a.dst + i * L.plane + L.at(gx, y)) = make_double2(fa[i], fb[i]);
-            } else {
+            for (int i = 0; i < Q; ++i)
+                *reinterpret_cast<double2*>(a.dst + i * L.plane + L.at(gx, y)) = make_double2(fa[i], fb[i]);
+        } else {
 #pragma unroll
-                for (int i = 0; i < Q; ++i) {
-                    if (!sa) a.dst[i * L.plane + L.at(gx, y)] = fa[i];
-                    if (!sb) a.dst[i * L.plane + L.at(gx, y + 1)] = fb[i];
-                }
+            for (int i = 0; i < Q; ++i) {
+                if (!sa) a.dst[i * L.plane + L.at(gx, y)] = fa[i];
+                if (!sb) a.dst[i * L.plane + L.at(gx, y + 1)] = fb[i];
             }
         }
     }
+    return bad;
+}
+
+template <bool PULL, bool FORCED>
+__global__ void __launch_bounds__(128) k_bulk_vec2(StepArgs a, int x_begin, int x_end) {
+    pdl_wait();
+    pdl_release();
+    const int y = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (y >= a.L.ny) return;
+    bool bad = false;
+    for (int x = x_begin + blockIdx.y; x < x_end; x += gridDim.y) bad |= bulk_vec2_column<PULL, FORCED>(a, x, y);
     if (bad) atomicMin(a.first_bad, a.bad_iter);
 }
 
@@ -193,6 +197,155 @@ __global__ void __launch_bounds__(128) k_edge(StepArgs a, BcArgs b, const unsign
     else
         collide_cell<false>(f, a.tau_inv, 0.0, 0.0);
     if (a.write) store_cell(a.dst, L, x + 1, y, f);
+}
+
+// ------------------------------------------------------------------------------------------
+// Edge columns + halo exchange in ONE kernel (P2pArgs in the header).  Protocol, per launch `seq`:
+//   1. wait until both neighbours have delivered exchange seq-1 (their counters in MY memory).  That
+//      also means they have finished reading the ghost columns this launch is about to overwrite in
+//      THEIR memory (the A-B pair alternates, so the ghost written now was read by their launch seq-1);
+//   2. compute the edge cells, store them locally and push the face-crossing populations into the
+//      neighbours' ghost columns (plain stores to peer memory: NVLink);
+//   3. __threadfence_system(), and the last block to finish publishes `seq` in the neighbours' memory.
+// No rank can run more than one exchange ahead of a neighbour, there is no cycle in the waits (launch
+// seq of one GPU only waits for launch seq-1 of another), and a spinning block never keeps another
+// GPU from making progress.
+__device__ __forceinline__ void spin_until(const int* flag, int want) {
+    while (*reinterpret_cast<const volatile int*>(flag) < want) __nanosleep(64);
+}
+
+// Steps 1 and 3 of the protocol for one block of edge work.
+__device__ __forceinline__ void p2p_block_begin(const P2pArgs& x) {
+    if (threadIdx.x == 0) {
+        if (x.peer_dst_west) spin_until(x.my_flags + 0, x.seq - 1);
+        if (x.peer_dst_east) spin_until(x.my_flags + 1, x.seq - 1);
+        __threadfence_system();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void p2p_block_end(const P2pArgs& x, unsigned int edge_blocks) {
+    __threadfence_system();  // this block's peer stores first
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(x.blocks_done, 1u) == edge_blocks - 1) {
+            *x.blocks_done = 0;
+            __threadfence_system();
+            if (x.west_flag) *reinterpret_cast<volatile int*>(x.west_flag) = x.seq;
+            if (x.east_flag) *reinterpret_cast<volatile int*>(x.east_flag) = x.seq;
+            __threadfence_system();
+        }
+    }
+}
+
+// Step 2 for one cell of edge column `col`.
+__device__ __forceinline__ void p2p_edge_cell(const StepArgs& a, const BcArgs& b, const unsigned char* __restrict__ mask, int pull,
+                                              const P2pArgs& x, int col, int y) {
+    const Layout& L = a.L;
+    double f[Q];
+    if (mask[L.at(col + 1, y)]) {
+#pragma unroll
+        for (int i = 0; i < Q; ++i) f[i] = b.w[i];
+    } else {
+        if (pull) {
+            load_cell<true>(a.src, L, col + 1, y, f);
+            double rho_bc, u_out;
+            apply_bc(f, col, y, L, b, rho_bc, u_out);
+            if (any_unstable(f)) atomicMin(a.first_bad, a.bad_iter);
+        } else {
+            load_cell<false>(a.src, L, col + 1, y, f);
+        }
+        if (a.forced)
+            collide_cell<true>(f, a.tau_inv, a.Fx, a.Fy);
+        else
+            collide_cell<false>(f, a.tau_inv, 0.0, 0.0);
+    }
+    store_cell(a.dst, L, col + 1, y, f);
+    // interior column lnx-1 -> the east neighbour's W ghost (1,5,8 move in +x); column 0 -> the west
+    // neighbour's E ghost (3,6,7).  With lnx == 1 the single column feeds both.
+    if (x.peer_dst_east && col == L.lnx - 1) {
+        x.peer_dst_east[1 * L.plane + L.at(0, y)] = f[1];
+        x.peer_dst_east[5 * L.plane + L.at(0, y)] = f[5];
+        x.peer_dst_east[8 * L.plane + L.at(0, y)] = f[8];
+    }
+    if (x.peer_dst_west && col == 0) {
+        x.peer_dst_west[3 * L.plane + L.at(L.lnx + 1, y)] = f[3];
+        x.peer_dst_west[6 * L.plane + L.at(L.lnx + 1, y)] = f[6];
+        x.peer_dst_west[7 * L.plane + L.at(L.lnx + 1, y)] = f[7];
+    }
+}
+
+// The edge work as the FIRST blocks of the bulk launch itself: blockIdx.y 0 and 1 are the two edge
+// columns (256 rows per block, two per thread), blockIdx.y >= 2 the interior columns.  The peer
+// stores and the flag hand-shake then cost nothing: they run under the 0.7 ms interior kernel.
+template <bool PULL, bool FORCED>
+__global__ void __launch_bounds__(128) k_bulk_vec2_p2p(StepArgs a, int x_begin, int x_end, BcArgs b,
+                                                       const unsigned char* __restrict__ mask, P2pArgs px) {
+    pdl_wait();
+    pdl_release();
+    const Layout& L = a.L;
+    if (blockIdx.y < 2) {
+        p2p_block_begin(px);
+        const int col = blockIdx.y == 0 ? 0 : L.lnx - 1;
+#pragma unroll 1
+        for (int r = 0; r < 2; ++r) {
+            const int y = blockIdx.x * 256 + r * 128 + threadIdx.x;
+            if (y < L.ny) p2p_edge_cell(a, b, mask, PULL ? 1 : 0, px, col, y);
+        }
+        p2p_block_end(px, gridDim.x * 2);
+        return;
+    }
+    const int y = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (y >= L.ny) return;
+    bool bad = false;
+    for (int x = x_begin + (blockIdx.y - 2); x < x_end; x += gridDim.y - 2) bad |= bulk_vec2_column<PULL, FORCED>(a, x, y);
+    if (bad) atomicMin(a.first_bad, a.bad_iter);
+}
+
+// Fallback for odd ny / the scalar variant.  Boundary fix-up of a slab with neighbours: the list-driven ring / solid work of k_fixup plus,
+// in the FIRST blocks of the grid, every cell of the two slab-edge columns with the halo exchange
+// fused in (steps 1-3 above).  The bulk kernel has already run over all columns; what it wrote into
+// the edge columns (computed from ghost columns that may not have been refreshed yet) is simply
+// overwritten here, exactly as for ring cells.
+__global__ void __launch_bounds__(128) k_fixup_p2p(StepArgs a, BcArgs b, int pull, const int2* __restrict__ ring, int n_ring,
+                                                   const int2* __restrict__ solids, int n_solid,
+                                                   const unsigned char* __restrict__ mask, P2pArgs px, int edge_blocks) {
+    pdl_wait();
+    pdl_release();
+    const Layout& L = a.L;
+    if ((int)blockIdx.x < edge_blocks) {
+        p2p_block_begin(px);
+        const int per_col = edge_blocks / (L.lnx > 1 ? 2 : 1);
+        const int col = (int)blockIdx.x < per_col ? 0 : L.lnx - 1;
+        const int y = ((int)blockIdx.x % per_col) * blockDim.x + threadIdx.x;
+        if (y < L.ny) p2p_edge_cell(a, b, mask, pull, px, col, y);
+        p2p_block_end(px, (unsigned int)edge_blocks);
+        return;
+    }
+    const int idx = (blockIdx.x - edge_blocks) * blockDim.x + threadIdx.x;
+    if (idx < n_ring) {
+        if (!pull) return;  // the first iteration collides f_current as it is
+        const int2 c = ring[idx];
+        double f[Q];
+        load_cell<true>(a.src, L, c.x + 1, c.y, f);
+        double rho_bc, u_out;
+        apply_bc(f, c.x, c.y, L, b, rho_bc, u_out);
+        if (any_unstable(f)) atomicMin(a.first_bad, a.bad_iter);
+        if (a.forced)
+            collide_cell<true>(f, a.tau_inv, a.Fx, a.Fy);
+        else
+            collide_cell<false>(f, a.tau_inv, 0.0, 0.0);
+        store_cell(a.dst, L, c.x + 1, c.y, f);
+    } else if (idx - n_ring < n_solid) {
+        const int2 c = solids[idx - n_ring];
+        store_cell(a.dst, L, c.x + 1, c.y, b.w);
+    }
+}
+
+__global__ void k_wait_halo(P2pArgs x) {
+    if (x.peer_dst_west) spin_until(x.my_flags + 0, x.seq);
+    if (x.peer_dst_east) spin_until(x.my_flags + 1, x.seq);
+    __threadfence_system();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -507,6 +660,32 @@ cudaError_t launch_fixup(bool pull, const StepArgs& a, const BcArgs& b, const in
 cudaError_t launch_edge(bool pull, const StepArgs& a, const BcArgs& b, const unsigned char* mask, cudaStream_t s) {
     dim3 grid(cdiv(a.L.ny, 128), a.L.lnx > 1 ? 2 : 1);
     return launch_chain(k_edge, grid, dim3(128), s, a, b, mask, pull ? 1 : 0);
+}
+
+bool bulk_p2p_supported(int variant, const StepArgs& a) { return variant != BULK_SCALAR && a.L.ny % 2 == 0 && a.L.lnx >= 4; }
+
+cudaError_t launch_bulk_p2p(bool pull, const StepArgs& a, const BcArgs& b, const unsigned char* mask, const P2pArgs& x,
+                            cudaStream_t s) {
+    const int x_begin = 1, x_end = a.L.lnx - 1, ncols = x_end - x_begin;
+    dim3 grid(cdiv(a.L.ny / 2, 128), (ncols < 65533 ? ncols : 65533) + 2);
+    if (pull)
+        return a.forced ? launch_chain(k_bulk_vec2_p2p<true, true>, grid, dim3(128), s, a, x_begin, x_end, b, mask, x)
+                        : launch_chain(k_bulk_vec2_p2p<true, false>, grid, dim3(128), s, a, x_begin, x_end, b, mask, x);
+    return a.forced ? launch_chain(k_bulk_vec2_p2p<false, true>, grid, dim3(128), s, a, x_begin, x_end, b, mask, x)
+                    : launch_chain(k_bulk_vec2_p2p<false, false>, grid, dim3(128), s, a, x_begin, x_end, b, mask, x);
+}
+
+cudaError_t launch_fixup_p2p(bool pull, const StepArgs& a, const BcArgs& b, const int2* ring, int n_ring, const int2* solids,
+                             int n_solid, const unsigned char* mask, const P2pArgs& x, cudaStream_t s) {
+    const int edge_blocks = cdiv(a.L.ny, 128) * (a.L.lnx > 1 ? 2 : 1);
+    const long long n = (long long)n_ring + n_solid;
+    return launch_chain(k_fixup_p2p, dim3(edge_blocks + cdiv(n, 128)), dim3(128), s, a, b, pull ? 1 : 0, ring, n_ring, solids,
+                        n_solid, mask, x, edge_blocks);
+}
+
+cudaError_t launch_wait_halo(const P2pArgs& x, cudaStream_t s) {
+    k_wait_halo<<<1, 1, 0, s>>>(x);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_forces(const double* f_next, const Link* links, int n_links, double* out, cudaStream_t s) {

@@ -51,6 +51,31 @@ cudaError_t launch_fixup(bool pull, const StepArgs& a, const BcArgs& b, const in
 // Both slab-edge columns in one launch (multi-slab jobs): pull, boundary rules, collide; solids = w.
 cudaError_t launch_edge(bool pull, const StepArgs& a, const BcArgs& b, const unsigned char* mask, cudaStream_t s);
 
+// The halo exchange fused into the boundary fix-up (multi-slab jobs with CUDA IPC peer access): every
+// edge cell also stores the three populations that cross its slab face straight into the
+// neighbouring GPU's ghost column over NVLink, and the launch synchronises with the neighbours
+// through step counters in peer memory -- no NCCL call, no second stream, no event in the step.
+struct P2pArgs {
+    double* peer_dst_west;  // the west neighbour's destination buffer (its E ghost column receives 3,6,7) or nullptr
+    double* peer_dst_east;  // the east neighbour's destination buffer (its W ghost column receives 1,5,8) or nullptr
+    int* my_flags;          // [0] last step whose halo arrived from the west, [1] from the east (written by the peers)
+    int* west_flag;         // -> the west neighbour's my_flags[1]
+    int* east_flag;         // -> the east neighbour's my_flags[0]
+    unsigned int* blocks_done;  // last-block detection
+    int seq;                    // exchange number of this launch (the same on every rank)
+};
+// Interior columns AND the fused edge + halo work in one launch (vectorised variant, even ny): the
+// peer stores and the hand-shake run under the interior kernel.
+bool bulk_p2p_supported(int variant, const StepArgs& a);
+cudaError_t launch_bulk_p2p(bool pull, const StepArgs& a, const BcArgs& b, const unsigned char* mask, const P2pArgs& x,
+                            cudaStream_t s);
+// Fallback (odd ny / scalar variant): ring / solid fix-up of the interior columns plus both slab-edge
+// columns with the fused exchange, after a bulk launch over every column.
+cudaError_t launch_fixup_p2p(bool pull, const StepArgs& a, const BcArgs& b, const int2* ring, int n_ring, const int2* solids,
+                             int n_solid, const unsigned char* mask, const P2pArgs& x, cudaStream_t s);
+// Blocks the stream until the halos of exchange `seq` have arrived from both neighbours.
+cudaError_t launch_wait_halo(const P2pArgs& x, cudaStream_t s);
+
 // Momentum-exchange reduction (reference include/LBMIO.h:114-162) over a precomputed link list.
 cudaError_t launch_forces(const double* f_next, const Link* links, int n_links, double* out_fx_fy, cudaStream_t s);
 

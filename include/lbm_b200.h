@@ -81,6 +81,8 @@ typedef struct lbm_info {
     int64_t bytes_per_buffer;    /* one SoA population buffer on the device */
     int32_t row_pitch;           /* doubles between consecutive x columns in a plane */
     int32_t kernel_variant;
+    int32_t halo_p2p;            /* 1: halo columns go by peer stores fused into the edge kernel (CUDA IPC over
+                                    NVLink); 0: NCCL send/recv (or a single slab) */
 } lbm_info;
 
 typedef struct lbm_solver* lbm_handle;

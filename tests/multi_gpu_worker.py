@@ -10,13 +10,15 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def main():
-    out_dir, steps, seed = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+    out_dir, steps, seed, case_name = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
     import torch.distributed as dist
 
     dist.init_process_group("gloo")  # only to hand the NCCL id around; the halo is the engine's own NCCL
     import lbm_b200
     import parity_util as util
-    from test_gpu_multi import CASE
+    from test_gpu_multi import CASES
+
+    CASE = CASES[case_name]
 
     params = util.case_to_params(CASE)
     s, slab = lbm_b200.create_slab_solver(params, dist)
@@ -31,7 +33,7 @@ def main():
     rho, ux, uy = s.macros()
     g = s.gather_macros()
     np.savez(os.path.join(out_dir, "slab%d.npz" % slab.rank), f_next=s.f_next()[1:-1, 1:-1], f_current=s.f_current()[1:-1, 1:-1],
-             rho=rho, ux=ux, uy=uy, rows=rows, bad=bad, forces_total=tot, maxvel=s.allreduce([s.max_velocity()], 2),
+             rho=rho, ux=ux, uy=uy, rows=rows, bad=bad, forces_total=tot, halo_p2p=s.info().halo_p2p, maxvel=s.allreduce([s.max_velocity()], 2),
              **({"g_rho": g[0], "g_ux": g[1], "g_uy": g[2]} if g is not None else {}))
     s.close()
     dist.barrier()

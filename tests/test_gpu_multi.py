@@ -13,7 +13,11 @@ import parity_util as util
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # the cylinder straddles the face between slabs 0 and 1 of a 2-slab run (x = 64)
-CASE = O.Case(nx=128, ny=48, cylinder_x=0.5, cylinder_radius=0.2, output_frequency=6, inlet_velocity=0.04)
+CASES = {
+    "even": O.Case(nx=128, ny=48, cylinder_x=0.5, cylinder_radius=0.2, output_frequency=6, inlet_velocity=0.04),
+    # odd ny: scalar bulk kernel, halo fused into the fix-up kernel instead of the bulk launch
+    "odd": O.Case(nx=128, ny=47, cylinder_x=0.5, cylinder_radius=0.2, output_frequency=6, inlet_velocity=0.04),
+}
 
 
 def n_gpus():
@@ -22,19 +26,22 @@ def n_gpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("overlap", ["1", "0"])
+@pytest.mark.parametrize("overlap", ["1", "0", "nccl"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("seed", [0, 5])
-def test_slabs_match_single_rank_oracle(tmp_path, world, overlap, seed):
+@pytest.mark.parametrize("seed,case_name", [(0, "even"), (5, "even"), (5, "odd")])
+def test_slabs_match_single_rank_oracle(tmp_path, world, overlap, seed, case_name):
+    CASE = CASES[case_name]
     if n_gpus() < world:
         pytest.skip("needs %d GPUs" % world)
     steps = 37
-    env = dict(os.environ, LBM_B200_OVERLAP=overlap)
+    # "1": edge kernel + halo fused over peer memory when CUDA IPC is available (else the NCCL path);
+    # "nccl": the overlapped NCCL send/recv path, forced; "0": exchange in stream order, no overlap
+    env = dict(os.environ, LBM_B200_OVERLAP="0" if overlap == "0" else "1", LBM_B200_P2P="0" if overlap == "nccl" else "1")
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         env.pop(k, None)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", str(29800 + os.getpid() % 150 + world), os.path.join(ROOT, "tests", "multi_gpu_worker.py"), str(tmp_path),
-           str(steps), str(seed)]
+           str(steps), str(seed), case_name]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     if seed:
@@ -49,6 +56,9 @@ def test_slabs_match_single_rank_oracle(tmp_path, world, overlap, seed):
         assert np.array_equal(got, want), "%s differs: max %.3e" % (key, np.abs(got - want).max())
     assert np.array_equal(parts[0]["g_rho"], o.rho) and np.array_equal(parts[0]["g_ux"], o.ux) and np.array_equal(parts[0]["g_uy"], o.uy)
     assert all(int(p["bad"]) == bad == -1 for p in parts)
+    if overlap == "nccl":
+        assert all(int(p["halo_p2p"]) == 0 for p in parts)
+    print("halo_p2p:", [int(p["halo_p2p"]) for p in parts])
     total = sum(p["rows"][:, 1:3] for p in parts)
     assert np.array_equal(parts[0]["rows"][:, 0], rows[:, 0]) and np.abs(total - rows[:, 1:3]).max() <= 1e-13
     ofx, ofy = o.forces()
