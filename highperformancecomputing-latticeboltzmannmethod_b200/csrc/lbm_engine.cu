@@ -519,15 +519,14 @@ int exchange(lbm_handle h, double* buf, cudaStream_t s) {
     const Layout& L = h->L;
     static const int to_east[3] = {1, 5, 8}, to_west[3] = {3, 6, 7};
     NC(h, N.GroupStart());
+    // NCCL pairs the sends and receives between two ranks in issue order.  With two slabs and
+    // periodic x the east and the west neighbour are the SAME rank: my east-going send has to meet
+    // its receive "from the west", so every rank issues send-east, recv-west, send-west, recv-east.
     for (int k = 0; k < 3; ++k) {
-        if (h->east >= 0) {
-            NC(h, N.Send(buf + to_east[k] * L.plane + L.at(L.lnx, 0), L.ny, ncclDouble, h->east, h->comm, s));
-            NC(h, N.Recv(buf + to_west[k] * L.plane + L.at(L.lnx + 1, 0), L.ny, ncclDouble, h->east, h->comm, s));
-        }
-        if (h->west >= 0) {
-            NC(h, N.Send(buf + to_west[k] * L.plane + L.at(1, 0), L.ny, ncclDouble, h->west, h->comm, s));
-            NC(h, N.Recv(buf + to_east[k] * L.plane + L.at(0, 0), L.ny, ncclDouble, h->west, h->comm, s));
-        }
+        if (h->east >= 0) NC(h, N.Send(buf + to_east[k] * L.plane + L.at(L.lnx, 0), L.ny, ncclDouble, h->east, h->comm, s));
+        if (h->west >= 0) NC(h, N.Recv(buf + to_east[k] * L.plane + L.at(0, 0), L.ny, ncclDouble, h->west, h->comm, s));
+        if (h->west >= 0) NC(h, N.Send(buf + to_west[k] * L.plane + L.at(1, 0), L.ny, ncclDouble, h->west, h->comm, s));
+        if (h->east >= 0) NC(h, N.Recv(buf + to_west[k] * L.plane + L.at(L.lnx + 1, 0), L.ny, ncclDouble, h->east, h->comm, s));
     }
     NC(h, N.GroupEnd());
     return LBM_OK;

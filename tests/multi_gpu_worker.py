@@ -20,7 +20,7 @@ def main():
 
     CASE = CASES[case_name]
 
-    params = util.case_to_params(CASE)
+    params = util.case_to_params(CASE, flags=1 if case_name == "periodic" else 0)
     s, slab = lbm_b200.create_slab_solver(params, dist)
     s.initialise()
     if seed:
