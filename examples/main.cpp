@@ -18,7 +18,7 @@
 namespace {
 void usage() {
     std::cout << "lbm_solver [--nx N] [--ny N] [--steps N] [--of N] [--tau X] [--uin X] [--cx X] [--cy X] [--cr X]\n"
-                 "           [--vtk 0|1] [--vtk-start N] [--sync-vtk] [--periodic-x] [--periodic-y] [--no-cylinder]\n"
+                 "           [--vtk 0|1] [--vtk-start N] [--sync-vtk] [--vtk-binary] [--periodic-x] [--periodic-y] [--no-cylinder]\n"
                  "           [--shear-wave] [--aa] [--fx X] [--fy X] [--no-final]\n"
                  "           [--checkpoint FILE] [--restart FILE]\n";
 }
@@ -43,6 +43,7 @@ int main(int argc, char* argv[]) {
         else if (k == "--vtk") vtk = std::atoi(val()) != 0;
         else if (k == "--vtk-start") params.vtk_start_step = std::atoi(val());
         else if (k == "--sync-vtk") params.async_vtk = false;
+        else if (k == "--vtk-binary") params.vtk_binary = true;
         else if (k == "--periodic-x") params.flags |= LBM_FLAG_PERIODIC_X;
         else if (k == "--periodic-y") params.flags |= LBM_FLAG_PERIODIC_Y;
         else if (k == "--no-cylinder") params.flags |= LBM_FLAG_NO_CYLINDER;

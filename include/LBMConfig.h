@@ -44,7 +44,8 @@ struct SimulationParams {
     int flags = 0;
     double body_force_x = 0.0;
     double body_force_y = 0.0;
-    bool async_vtk = true;  // VTK frames leave through pinned snapshots + a writer thread
+    bool async_vtk = true;   // VTK frames leave through pinned snapshots + a writer thread
+    bool vtk_binary = false;  // legacy-VTK BINARY frames instead of the reference's ASCII ones
 
     // kinematic viscosity and Reynolds number exactly as the reference derives them (:54-58);
     // note Re uses the real-valued diameter 2*cylinder_radius*ny, C_D/C_L the integer one

@@ -209,6 +209,42 @@ class IOManager {
         std::fclose(f);
     }
 
+    // Extension: the same frame as legacy-VTK BINARY (big-endian doubles), 42 MB instead of 51 MB at
+    // 2048 x 512 and no decimal formatting; ParaView reads both.  Chosen by params.vtk_binary.
+    static void write_vtk_arrays_binary(const double* ux, const double* uy, const double* rho, int nx, int ny, int timestep) {
+        char filename[256];
+        std::snprintf(filename, sizeof(filename), "vtk_output/lbm_%06d.vtk", timestep);
+        std::FILE* f = std::fopen(filename, "wb");
+        if (!f) {
+            std::cerr << "ERROR: Cannot write " << filename << "\n";
+            return;
+        }
+        std::fprintf(f, "# vtk DataFile Version 3.0\nLBM Flow Timestep %d\nBINARY\nDATASET STRUCTURED_POINTS\n", timestep);
+        std::fprintf(f, "DIMENSIONS %d %d 1\nORIGIN 0 0 0\nSPACING 1 1 1\nPOINT_DATA %d\n", nx, ny, nx * ny);
+        const size_t n = (size_t)nx * ny;
+        auto big_endian = [](double v) {
+            uint64_t b;
+            std::memcpy(&b, &v, 8);
+            return __builtin_bswap64(b);
+        };
+        std::vector<uint64_t> buf(3 * n);
+        std::fputs("VECTORS velocity double\n", f);
+        for (size_t k = 0; k < n; ++k) {
+            buf[3 * k] = big_endian(ux[k]);
+            buf[3 * k + 1] = big_endian(uy[k]);
+            buf[3 * k + 2] = big_endian(0.0);
+        }
+        std::fwrite(buf.data(), 8, 3 * n, f);
+        std::fputs("\nSCALARS velocity_magnitude double\nLOOKUP_TABLE default\n", f);
+        for (size_t k = 0; k < n; ++k) buf[k] = big_endian(std::sqrt(ux[k] * ux[k] + uy[k] * uy[k]));
+        std::fwrite(buf.data(), 8, n, f);
+        std::fputs("\nSCALARS density double\nLOOKUP_TABLE default\n", f);
+        for (size_t k = 0; k < n; ++k) buf[k] = big_endian(rho[k]);
+        std::fwrite(buf.data(), 8, n, f);
+        std::fputs("\n", f);
+        std::fclose(f);
+    }
+
     // velocity_field.csv, simulation_params.csv and the force-coefficient summary (reference
     // :194-219).  forces.csv is flushed first so that every row takes part in the averages (the
     // reference re-reads the file while its stream is still buffered, :367-372).
@@ -338,7 +374,7 @@ class IOManager {
 // images are still being written (the ASCII format, not the GPU, is then the bottleneck).
 class FrameWriter {
    public:
-    explicit FrameWriter(const Grid& grid) : grid_(grid) {}
+    explicit FrameWriter(const Grid& grid, bool binary = false) : grid_(grid), binary_(binary) {}
     ~FrameWriter() { finish(); }
 
     void submit(int timestep) {
@@ -411,7 +447,10 @@ class FrameWriter {
             if (j.wait_slot) lbm_snapshot_wait_slot(grid_.handle(), j.slot);
             const size_t n = (size_t)grid_.global_nx() * grid_.global_ny();
             const double* img = image_[j.slot];
-            IOManager::write_vtk_arrays(img + n, img + 2 * n, img, grid_.global_nx(), grid_.global_ny(), j.timestep);
+            if (binary_)
+                IOManager::write_vtk_arrays_binary(img + n, img + 2 * n, img, grid_.global_nx(), grid_.global_ny(), j.timestep);
+            else
+                IOManager::write_vtk_arrays(img + n, img + 2 * n, img, grid_.global_nx(), grid_.global_ny(), j.timestep);
             {
                 std::lock_guard<std::mutex> lk(m_);
                 busy_[j.slot] = false;
@@ -422,6 +461,7 @@ class FrameWriter {
     }
 
     const Grid& grid_;
+    bool binary_ = false;
     double* image_[2] = {nullptr, nullptr};
     bool busy_[2] = {false, false};
     std::deque<Job> jobs_;

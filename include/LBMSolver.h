@@ -50,7 +50,7 @@ class Solver {
         const int T = params_.num_timesteps;
         const int of = std::max(params_.output_frequency, 1);
         std::unique_ptr<FrameWriter> frames;
-        if (enable_vtk_output_ && params_.async_vtk) frames = std::make_unique<FrameWriter>(grid_);
+        if (enable_vtk_output_ && params_.async_vtk) frames = std::make_unique<FrameWriter>(grid_, params_.vtk_binary);
 
         int t = first_timestep_;
         while (t < T) {
@@ -105,7 +105,12 @@ class Solver {
             uy.resize(n);
         }
         grid_.check(lbm_gather_macros(grid_.handle(), rho.data(), ux.data(), uy.data()));
-        if (grid_.mpi_rank() == 0) IOManager::write_vtk_timestep(ux, uy, rho, params_, timestep);
+        if (grid_.mpi_rank() == 0) {
+            if (params_.vtk_binary)
+                IOManager::write_vtk_arrays_binary(ux.data(), uy.data(), rho.data(), params_.nx, params_.ny, timestep);
+            else
+                IOManager::write_vtk_timestep(ux, uy, rho, params_, timestep);
+        }
     }
 
     SimulationParams params_;

@@ -50,7 +50,8 @@ static int check_fixed8(long count, unsigned seed) {
 
 int main(int argc, char** argv) {
     if (argc >= 4 && !std::strcmp(argv[1], "fixed8")) return check_fixed8(std::atol(argv[2]), (unsigned)std::atoi(argv[3]));
-    if (argc >= 6 && !std::strcmp(argv[1], "vtk")) {
+    if (argc >= 6 && (!std::strcmp(argv[1], "vtk") || !std::strcmp(argv[1], "vtkbin"))) {
+        const bool binary = !std::strcmp(argv[1], "vtkbin");
         const int nx = std::atoi(argv[2]), ny = std::atoi(argv[3]), t = std::atoi(argv[5]);
         std::mt19937_64 rng((unsigned)std::atoi(argv[4]));
         std::uniform_real_distribution<double> u(-0.2, 0.2);
@@ -64,7 +65,10 @@ int main(int argc, char** argv) {
         LBM::SimulationParams p;
         p.nx = nx;
         p.ny = ny;
-        LBM::IOManager::write_vtk_timestep(ux, uy, rho, p, t);
+        if (binary)
+            LBM::IOManager::write_vtk_arrays_binary(ux.data(), uy.data(), rho.data(), nx, ny, t);
+        else
+            LBM::IOManager::write_vtk_timestep(ux, uy, rho, p, t);
         std::FILE* f = std::fopen("field.bin", "wb");
         std::fwrite(rho.data(), 8, rho.size(), f);
         std::fwrite(ux.data(), 8, ux.size(), f);

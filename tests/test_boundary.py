@@ -119,6 +119,28 @@ def test_vtk_frame_is_byte_identical_to_the_reference_format(host_checks, tmp_pa
     assert got == want
 
 
+def test_binary_vtk_frame_round_trips(host_checks, tmp_path):
+    nx, ny, t = 37, 23, 280
+    subprocess.run([host_checks, "vtkbin", str(nx), str(ny), "5", str(t)], cwd=tmp_path, check=True)
+    rho, ux, uy = np.fromfile(tmp_path / "field.bin").reshape(3, ny * nx)
+    raw = open(tmp_path / "vtk_output" / ("lbm_%06d.vtk" % t), "rb").read()
+    head = ("# vtk DataFile Version 3.0\nLBM Flow Timestep %d\nBINARY\nDATASET STRUCTURED_POINTS\nDIMENSIONS %d %d 1\n"
+            "ORIGIN 0 0 0\nSPACING 1 1 1\nPOINT_DATA %d\nVECTORS velocity double\n" % (t, nx, ny, nx * ny)).encode()
+    assert raw.startswith(head)
+    n, pos = nx * ny, len(head)
+    vec = np.frombuffer(raw, dtype=">f8", count=3 * n, offset=pos).reshape(n, 3)
+    assert np.array_equal(vec[:, 0], ux) and np.array_equal(vec[:, 1], uy) and not vec[:, 2].any()
+    pos += 24 * n
+    tag = b"\nSCALARS velocity_magnitude double\nLOOKUP_TABLE default\n"
+    assert raw[pos:pos + len(tag)] == tag
+    pos += len(tag)
+    assert np.array_equal(np.frombuffer(raw, dtype=">f8", count=n, offset=pos), np.sqrt(ux * ux + uy * uy))
+    pos += 8 * n
+    tag = b"\nSCALARS density double\nLOOKUP_TABLE default\n"
+    assert raw[pos:pos + len(tag)] == tag
+    assert np.array_equal(np.frombuffer(raw, dtype=">f8", count=n, offset=pos + len(tag)), rho)
+
+
 def test_forces_csv_rows(host_checks, tmp_path):
     rows = [(0, 1.53739333123, -4.5e-16), (140, 0.21697769, 0.0), (10000, -0.05162555, 1.25e-9)]
     inp = "".join("%d %.17g %.17g\n" % r for r in rows)
