@@ -90,7 +90,7 @@ def test_bootstrap_env_single_and_multi(built, tmp_path):
 @pytest.fixture(scope="session")
 def host_checks(built, tmp_path_factory):
     exe = str(tmp_path_factory.mktemp("cpp") / "host_checks")
-    subprocess.run(["g++", "-std=c++17", "-O2", "-mfma", "-pthread", "-I" + INC, os.path.join(ROOT, "tests", "cpp", "host_checks.cpp"),
+    subprocess.run(["g++", "-std=c++17", "-O2", "-mfma", "-ffp-contract=off", "-pthread", "-I" + INC, os.path.join(ROOT, "tests", "cpp", "host_checks.cpp"),
                     "-o", exe, "-L" + PKG, "-llbm_b200", "-Wl,-rpath," + PKG], check=True)
     return exe
 
@@ -161,7 +161,7 @@ def test_reference_main_cpp_compiles_unchanged_against_the_dropin_headers(built,
     shutil.copy(os.path.join(REF, "src", "main.cpp"), tmp_path / "src" / "main.cpp")
     os.symlink(INC, tmp_path / "include")
     exe = tmp_path / "lbm_solver_ref_main"
-    r = subprocess.run(["g++", "-std=c++17", "-O1", "-mfma", "-pthread", "-I" + os.path.join(INC, "mpi_compat"), "-I" + INC,
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-mfma", "-ffp-contract=off", "-pthread", "-I" + os.path.join(INC, "mpi_compat"), "-I" + INC,
                         str(tmp_path / "src" / "main.cpp"), "-o", str(exe), "-L" + PKG, "-llbm_b200", "-Wl,-rpath," + PKG],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]

@@ -147,7 +147,7 @@ def test_grid_accessors_follow_the_reference_conventions(tmp_path, poke):
     getters, the writable f_current used for a caller-defined initial state) against the oracle."""
     pkg = os.path.join(ROOT, "highperformancecomputing-latticeboltzmannmethod_b200")
     exe = str(tmp_path / "grid_api_dump")
-    subprocess.run(["g++", "-std=c++17", "-O1", "-mfma", "-pthread", "-I" + os.path.join(ROOT, "include"),
+    subprocess.run(["g++", "-std=c++17", "-O1", "-mfma", "-ffp-contract=off", "-pthread", "-I" + os.path.join(ROOT, "include"),
                     os.path.join(ROOT, "tests", "cpp", "grid_api_dump.cpp"), "-o", exe, "-L" + pkg, "-llbm_b200", "-Wl,-rpath," + pkg], check=True)
     nx, ny, steps = 48, 20, 23
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
