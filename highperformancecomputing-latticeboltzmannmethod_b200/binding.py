@@ -116,6 +116,11 @@ def load():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
+        # a fresh checkout: compile the sm_100a library in place (nvcc needs no GPU); still no library -> fail loudly
+        import subprocess
+
+        subprocess.run(["make", "-C", os.path.join(PKG_DIR, "csrc"), "-j4"], capture_output=True)
+    if not os.path.exists(LIB_PATH):
         raise LbmError(-2, "liblbm_b200.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
     L = C.CDLL(LIB_PATH)
     H, D, I = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)

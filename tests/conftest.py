@@ -36,6 +36,15 @@ def pytest_collection_modifyitems(config, items):
                 item.add_marker(pytest.mark.skip(reason="no CUDA device visible"))
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _built_once():
+    """Build the C-ABI library, the oracle and the example driver if a fresh checkout lacks them
+    (a no-op `make` otherwise).  nvcc cross-compiles without a GPU."""
+    import __graft_entry__ as g
+
+    g.build()
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
