@@ -1,7 +1,9 @@
 // lbm_engine.cu -- host side of liblbm_b200.so: the slab object behind an lbm_handle, the step
 // scheduler (what Solver::run's loop body becomes, reference include/LBMSolver.h:48-76), the halo
-// exchange (Grid::exchange_ghost_cells, include/LBMGrid.h:249-283 -> NCCL send/recv of the three
-// populations that cross each slab face), and the extern "C" entry points of include/lbm_b200.h.
+// exchange (Grid::exchange_ghost_cells, include/LBMGrid.h:249-283 -> the three populations that cross
+// each slab face, stored into the neighbour GPU's ghost column by the step kernel itself over CUDA-IPC
+// peer memory, or sent by NCCL where IPC is unavailable), and the extern "C" entry points of
+// include/lbm_b200.h.
 //
 // State convention.  After t >= 1 reference iterations buffer f[cur] holds
 // the POST-COLLISION populations f_next of iteration t-1 and f[cur^1] still holds the state the
@@ -44,7 +46,7 @@ struct lbm_solver {
     bool periodic_x = false, periodic_y = false;
 
     cudaStream_t stream = nullptr, copy_stream = nullptr, comm_stream = nullptr;
-    cudaEvent_t ev_macros = nullptr, ev_snapshot = nullptr, ev_edge = nullptr, ev_comm = nullptr, ev_main = nullptr;
+    cudaEvent_t ev_macros = nullptr, ev_snapshot = nullptr, ev_edge = nullptr, ev_comm = nullptr;
     bool snapshot_pending = false;
     cudaEvent_t ev_slot[LBM_SNAPSHOT_SLOTS] = {};  // completion of the D2H copies of lbm_snapshot_begin_slot
 
@@ -59,7 +61,7 @@ struct lbm_solver {
     int n_ring = 0;
     int2* d_solids = nullptr;
     int n_solid = 0;
-    int n_ring_edge = 0, n_solid_edge = 0;  // leading entries that lie in columns 0 / lnx-1
+    int n_ring_edge = 0;  // leading ring entries that lie in columns 0 / lnx-1 (the edge kernels redo those columns)
     // Per-column solid runs (StepArgs::cols): where the solid cells of a column form one run the
     // bulk kernels never store them, so they keep w without any reset.  The solid list is ordered
     // [cells of columns without such a run][layer-1 cells: a non-solid neighbour][the rest]:
@@ -312,7 +314,6 @@ int build_geometry(lbm_handle h) {
                 h->col_lo = std::min(h->col_lo, x);
                 h->col_hi = std::max(h->col_hi, x + 1);
             }
-        h->n_solid_edge = 0;  // edge-column solids need no separate treatment any more (k_edge goes by the mask)
     }
     // links, in the reference's (y, x, i) order over solid cells
     for (int y = 0; y < L.ny; ++y)
@@ -639,7 +640,7 @@ int step_one(lbm_handle h) {
         if (!fused) {
             CU(h, bulk(0, L.lnx));
             CU(h, launch_fixup_p2p(pull, a, h->bc, h->d_ring + h->n_ring_edge, h->n_ring - h->n_ring_edge,
-                                   h->d_solids + h->n_solid_edge, solids_to_reset(h, pull, false) - h->n_solid_edge, h->d_mask,
+                                   h->d_solids, solids_to_reset(h, pull, false), h->d_mask,
                                    px, h->stream));
         } else {
             if (h->time_bulk && (h->iter % h->time_bulk) == 0) {
@@ -657,7 +658,7 @@ int step_one(lbm_handle h) {
                 CU(h, launch_bulk_p2p(pull, a, h->bc, h->d_mask, px, h->stream));
             }
             CU(h, launch_fixup(pull, a, h->bc, h->d_ring + h->n_ring_edge, h->n_ring - h->n_ring_edge,
-                               h->d_solids + h->n_solid_edge, solids_to_reset(h, pull, false) - h->n_solid_edge, h->stream));
+                               h->d_solids, solids_to_reset(h, pull, false), h->stream));
         }
         h->launches += 2;
     } else if (split) {
@@ -669,7 +670,7 @@ int step_one(lbm_handle h) {
         // exchange it depends on was issued, so its wait is satisfied long before it is reached.
         CU(h, bulk(1, L.lnx - 1));
         CU(h, launch_fixup(pull, a, h->bc, h->d_ring + h->n_ring_edge, h->n_ring - h->n_ring_edge,
-                           h->d_solids + h->n_solid_edge, solids_to_reset(h, pull, false) - h->n_solid_edge, h->stream));
+                           h->d_solids, solids_to_reset(h, pull, false), h->stream));
         CU(h, cudaStreamWaitEvent(h->stream, h->ev_comm, 0));
         CU(h, launch_edge(pull, a, h->bc, h->d_mask, h->stream));
         CU(h, cudaEventRecord(h->ev_edge, h->stream));
@@ -857,7 +858,6 @@ int create_common(const lbm_params* p, int device, int rank, int world, const vo
     CUC(cudaEventCreateWithFlags(&h->ev_snapshot, cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&h->ev_edge, cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
-    CUC(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
     const size_t fbytes = (size_t)h->L.plane * Q * sizeof(double);
     CUC(cudaMalloc(&h->f[0], fbytes));
     CUC(cudaMemsetAsync(h->f[0], 0, fbytes, h->stream));
@@ -883,7 +883,6 @@ int create_common(const lbm_params* p, int device, int rank, int world, const vo
     CUC(cudaStreamSynchronize(h->stream));
     CUC(cudaEventRecord(h->ev_comm, h->comm_stream));
     CUC(cudaEventRecord(h->ev_edge, h->comm_stream));
-    CUC(cudaEventRecord(h->ev_main, h->stream));
 #undef CUC
     if (world > 1) {
         const NcclApi& N = nccl_api();
@@ -977,7 +976,6 @@ int lbm_destroy(lbm_handle h) {
     if (h->ev_snapshot) cudaEventDestroy(h->ev_snapshot);
     if (h->ev_edge) cudaEventDestroy(h->ev_edge);
     if (h->ev_comm) cudaEventDestroy(h->ev_comm);
-    if (h->ev_main) cudaEventDestroy(h->ev_main);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
