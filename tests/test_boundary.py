@@ -195,3 +195,20 @@ def test_bootstrap_env_hands_the_nccl_id_to_every_rank(built, tmp_path):
     assert [o[0] for o in outs] == ["0", "0"], outs
     assert outs[0][1:3] == ["1", "2"] and outs[1][1:3] == ["0", "2"]
     assert outs[0][3] == outs[1][3] and len(outs[0][3]) == 256 and set(outs[0][3]) != {"0"}
+
+
+def test_config_header_matches_the_reference_header(tmp_path):
+    """LBM::SimulationParams / lattice tables (SURVEY.md row a1): the same program compiled against this
+    repo's LBMConfig.h and against the reference's prints the same text."""
+    src = os.path.join(ROOT, "tests", "cpp", "params_dump.cpp")
+    ours = str(tmp_path / "ours")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-I" + INC, src, "-o", ours], check=True)
+    out = subprocess.run([ours], capture_output=True, text=True, check=True).stdout
+    assert "Q 9 D 2" in out and "defaults 0.59999999999999998 0.01333 2048 512 120000 140" in out
+    # default case: Re = 20.47 (SURVEY.md F7), cylinder (409, 256), r = 25
+    nu = (0.6 - 0.5) / 3.0
+    assert "derived %.17g %.17g 409 256 25" % (nu, 0.01333 * (2.0 * 0.05 * 512) / nu) in out
+    if os.path.exists(os.path.join(REF, "include", "LBMConfig.h")):
+        theirs = str(tmp_path / "theirs")
+        subprocess.run(["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-I" + os.path.join(REF, "include"), src, "-o", theirs], check=True)
+        assert subprocess.run([theirs], capture_output=True, text=True, check=True).stdout == out
