@@ -15,18 +15,20 @@ inline double equilibrium_scalar(double rho, double ux, double uy) {
     return W_REST * rho * (1.0 - 1.5 * (ux * ux + uy * uy));
 }
 
-// All nine equilibria with the evaluation order of the reference's AVX2 routine
-// (include/LBMUtils.h:22-65): (w rho) * (((1 + 3 cu) - 1.5 u^2) + 4.5 cu^2).
+// The eight moving-population equilibria, f_eq[k] for direction i = k + 1, with the output convention
+// and the evaluation order of the reference's AVX2 routine (include/LBMUtils.h:22-65):
+// (w rho) * (((1 + 3 cu) - 1.5 u^2) + 4.5 cu^2).  The rest population is equilibrium_scalar().
 inline void equilibrium_simd(double rho, double ux, double uy, double* f_eq) {
     const double usq15 = 1.5 * (ux * ux + uy * uy);
-    f_eq[0] = equilibrium_scalar(rho, ux, uy);
     for (int i = 1; i < Q; ++i) {
         const double cu = VELOCITIES[i][0] * ux + VELOCITIES[i][1] * uy;
-        f_eq[i] = (WEIGHTS[i] * rho) * (((1.0 + 3.0 * cu) - usq15) + 4.5 * (cu * cu));
+        f_eq[i - 1] = (WEIGHTS[i] * rho) * (((1.0 + 3.0 * cu) - usq15) + 4.5 * (cu * cu));
     }
 }
 
-// include/LBMUtils.h:129-131 together with the bounds of include/LBMGrid.h:297-307.
-inline bool is_stable(const double value) { return std::isfinite(value) && value >= -1e5 && value <= 1e5; }
+// The scalar predicate of include/LBMUtils.h:129-131.  (Grid::check_stability's vector path,
+// include/LBMGrid.h:297-307, which the device kernels follow, flags v > 1e5 or v < -1e5 instead;
+// the two differ only for |v| == 1e5 exactly.)
+inline bool is_stable(const double value) { return std::isfinite(value) && std::abs(value) < 1e5; }
 
 }  // namespace LBM

@@ -212,3 +212,16 @@ def test_config_header_matches_the_reference_header(tmp_path):
         theirs = str(tmp_path / "theirs")
         subprocess.run(["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-I" + os.path.join(REF, "include"), src, "-o", theirs], check=True)
         assert subprocess.run([theirs], capture_output=True, text=True, check=True).stdout == out
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "include", "LBMUtils.h")), reason="reference not mounted")
+def test_utils_header_matches_the_reference_header(tmp_path):
+    """equilibrium_scalar / equilibrium_simd (8 outputs for i = 1..8) / is_stable: same values, bit for bit,
+    as the reference's AVX2 versions built without FP contraction."""
+    src = os.path.join(ROOT, "tests", "cpp", "utils_dump.cpp")
+    outs = []
+    for name, inc, std in (("ours", INC, "c++17"), ("theirs", os.path.join(REF, "include"), "c++20")):
+        exe = str(tmp_path / name)
+        subprocess.run(["g++", "-std=" + std, "-O1", "-mavx2", "-mfma", "-ffp-contract=off", "-I" + inc, src, "-o", exe], check=True)
+        outs.append(subprocess.run([exe], capture_output=True, text=True, check=True).stdout)
+    assert outs[0] == outs[1], "\n".join(outs)
