@@ -54,6 +54,10 @@ class Grid {
     Grid(const Grid&) = delete;
     Grid& operator=(const Grid&) = delete;
 
+    // ---- index helpers of the host-side views (reference :105-111) ----
+    size_t get_f_index(int x, int y, int i) const { return f_index(x, y, i); }
+    size_t get_interior_index(int x, int y) const { return m_index(x, y); }
+
     // ---- population accessors, ghost-inclusive coordinates (reference :115-121) ----
     const double& f_current(int x, int y, int i) const { return fetch(LBM_F_CURRENT)[f_index(x, y, i)]; }
     const double& f_next(int x, int y, int i) const { return fetch(LBM_F_NEXT)[f_index(x, y, i)]; }
