@@ -168,6 +168,16 @@ def ncu_traffic_per_launch(workload_name: str):
         return None
 
 
+def cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def host_cores() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -283,7 +293,7 @@ def main():
                        "inlet_velocity": cfg["inlet_velocity"], "output_frequency": cfg["output_frequency"],
                        "layout": "fp64 AoS (reference include/LBMGrid.h:105-107), host DRAM",
                        "partition": "1 process, OpenMP over %d host cores" % cores, "l2": "inputs_exceed_host_caches"},
-            "cpu_baseline": {"value": mlups, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "cpu_baseline": {"value": mlups, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "cpu_model": cpu_model()},
             "e2e": {"value": mlups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
         }
@@ -434,7 +444,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             v, cores, kind, sample, _ = run_reference(cfg, 20, 3, budget_s=30.0)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "cpu_model": cpu_model()}
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": host_cores(), "kind": "reference", "sample": "failed: %s" % e}
 
