@@ -22,7 +22,7 @@ FLAG_SHEAR_WAVE_INIT = 8
 FLAG_AA = 16
 
 F_CURRENT, F_NEXT = 0, 1
-VARIANT_SCALAR, VARIANT_VEC2 = 0, 1
+VARIANT_SCALAR, VARIANT_VEC2, VARIANT_TB = 0, 1, 2
 
 
 class LbmError(RuntimeError):
@@ -55,7 +55,8 @@ class CInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "abi_version", "global_nx", "global_ny", "local_nx", "local_ny", "x_start", "y_start", "rank", "world",
         "device", "cyl_x", "cyl_y", "cyl_r", "solid_cells", "links", "iteration")] + [
-        ("bytes_per_buffer", C.c_int64), ("row_pitch", C.c_int32), ("kernel_variant", C.c_int32), ("halo_p2p", C.c_int32)]
+        ("bytes_per_buffer", C.c_int64), ("row_pitch", C.c_int32), ("kernel_variant", C.c_int32), ("halo_p2p", C.c_int32),
+        ("pass_depth", C.c_int32), ("deep_solid_cells", C.c_int32)]
 
 
 @dataclass
@@ -105,6 +106,7 @@ EXPORTS = [
     "lbm_upload_f", "lbm_snapshot_begin", "lbm_snapshot_wait", "lbm_host_alloc", "lbm_host_free", "lbm_time_steps",
     "lbm_set_kernel_variant", "lbm_device_count", "lbm_get_counters", "lbm_event_record", "lbm_event_elapsed",
     "lbm_bootstrap_env", "lbm_set_params", "lbm_snapshot_begin_slot", "lbm_snapshot_wait_slot", "lbm_allreduce", "lbm_gather_macros",
+    "lbm_get_bulk_updates", "lbm_set_pass_depth",
 ]
 
 _lib = None
@@ -160,6 +162,8 @@ def load():
     L.lbm_set_params.argtypes = [H, C.POINTER(CParams)]
     L.lbm_allreduce.argtypes = [H, D, C.c_int, C.c_int]
     L.lbm_gather_macros.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.lbm_get_bulk_updates.argtypes = [H, LL]
+    L.lbm_set_pass_depth.argtypes = [H, C.c_int]
     for name in EXPORTS:
         if name != "lbm_last_error":
             getattr(L, name).restype = C.c_int
@@ -363,6 +367,16 @@ class Solver:
 
     def set_kernel_variant(self, v: int):
         self._ck(load().lbm_set_kernel_variant(self._h, v))
+
+    def set_pass_depth(self, d: int):
+        """Iterations per temporally blocked pass (kernel variant 2): 1, 2 (default) or 3."""
+        self._ck(load().lbm_set_pass_depth(self._h, d))
+
+    def bulk_updates(self) -> int:
+        """Cell updates of the bulk launches the last time_steps(per_kernel) timed."""
+        a = C.c_longlong()
+        self._ck(load().lbm_get_bulk_updates(self._h, C.byref(a)))
+        return a.value
 
 
 def device_count() -> int:

@@ -29,6 +29,7 @@
 #include "lbm_kernels.cuh"
 #include "lbm_layout.h"
 #include "lbm_nccl.h"
+#include "lbm_tb.cuh"
 
 using namespace lbm;
 
@@ -77,6 +78,17 @@ struct lbm_solver {
 
     double *d_rho = nullptr, *d_ux = nullptr, *d_uy = nullptr;
     bool macros_valid = false;
+    // Temporal blocking (variant BULK_TB, lbm_tb.cuh): passes of up to tb_depth iterations.  `lag` is the
+    // number of iterations between f[cur ^ 1] and f[cur] (the observers of rho / u want 1); the last stage
+    // of a pass can emit the moments its collision read in the slab's native order (d_m*), valid for the
+    // state after iteration macros_native_iter - 1.
+    int tb_depth = 2;
+    int lag = 1;
+    double *d_mrho = nullptr, *d_mux = nullptr, *d_muy = nullptr;
+    int macros_native_iter = -1;
+    bool emit_last = false;  // lbm_run: the last pass of the call emits (the caller will look at the fields)
+    int mask_lo = 0, mask_hi = 0;  // padded columns gx in [lo, hi) hold solid cells
+    long long n_deep = 0;          // interior solid cells whose eight neighbours are solid (never touched)
     double* d_scratch = nullptr;  // padded AoS staging for lbm_download_f / lbm_upload_f
     unsigned long long* d_maxbits = nullptr;
 
@@ -97,7 +109,7 @@ struct lbm_solver {
 
     BcArgs bc{};
     double init_u = 0.0;
-    int variant = BULK_VEC2;
+    int variant = BULK_TB;
     bool overlap = true;
 
     ncclComm_t comm = nullptr;
@@ -109,6 +121,9 @@ struct lbm_solver {
     int* peer_flags[2] = {nullptr, nullptr};
     void* ipc_opened[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     int edge_seq = 0;                    // exchanges issued so far (identical on every rank)
+    int* d_status = nullptr;             // non-zero: a halo wait timed out (lbm_device.cuh); sticky
+    unsigned long long halo_timeout_ns = 30ull * 1000000000ull;
+    bool halo_failed = false;
     double* d_red = nullptr;       // small device scratch for lbm_allreduce
     double* d_gather = nullptr;    // rank 0: one slab of rho/ux/uy received from a peer
     int* d_first_bad_all = nullptr;
@@ -118,6 +133,7 @@ struct lbm_solver {
     std::vector<cudaEvent_t> bulk_events;  // pairs, only while per-kernel timing is on
     int time_bulk = 0;  // 0 = off, n = events around the bulk launch of every n-th iteration
     long long bulk_timed_launches = 0, bulk_timed_cells = 0;  // of the last lbm_time_steps(per_kernel)
+    long long bulk_timed_updates = 0;                         // cell updates of those launches (cells x pass depth)
     cudaEvent_t marks[LBM_EVENT_SLOTS] = {};                  // lbm_event_record / lbm_event_elapsed
 
     std::string err;
@@ -243,10 +259,16 @@ int build_geometry(lbm_handle h) {
     };
     std::vector<int2> solids, ring;
     std::vector<Link> links, links_rev, links_nat;
-    for (int gx = 0; gx < L.lnx + 2; ++gx)
+    h->mask_lo = L.lnx + 2 + Layout::XO;
+    h->mask_hi = -Layout::XO;
+    for (int gx = -Layout::XO; gx < L.lnx + 2 + Layout::XO; ++gx)  // the wide ghost columns of lbm_tb.cuh included
         for (int y = -1; y <= L.ny; ++y) {
             const bool s = solid_global(L.x_start + gx - 1, y);
             h->h_mask[L.at(gx, y)] = s ? 1 : 0;
+            if (s) {
+                h->mask_lo = std::min(h->mask_lo, gx);
+                h->mask_hi = std::max(h->mask_hi, gx + 1);
+            }
             if (s && gx >= 1 && gx <= L.lnx && y >= 0 && y < L.ny) solids.push_back(make_int2(gx - 1, y));
         }
     // ring: fluid cells that get a boundary rule between pull and collide
@@ -386,6 +408,23 @@ int build_geometry(lbm_handle h) {
     h->n_ring = (int)ring.size();
     h->n_solid = (int)solids.size();
     h->n_links = (int)links.size();
+    {
+        // 2 = solid with eight solid neighbours: pulls nothing but w, is never checked, computed or stored
+        // (every other kernel only asks "non-zero?")
+        std::vector<unsigned char> m2 = h->h_mask;
+        h->n_deep = 0;
+        for (int gx = -Layout::XO + 1; gx < L.lnx + 1 + Layout::XO; ++gx)
+            for (int y = 0; y < L.ny; ++y) {
+                if (!h->h_mask[L.at(gx, y)]) continue;
+                bool deep = true;
+                for (int i = 1; i < Q && deep; ++i) deep = h->h_mask[L.at(gx - cxi(i), y - cyi(i))] != 0;
+                if (deep) {
+                    m2[L.at(gx, y)] = 2;
+                    if (gx >= 1 && gx <= L.lnx) h->n_deep += 1;
+                }
+            }
+        h->h_mask.swap(m2);
+    }
     CU(h, cudaMemcpyAsync(h->d_mask, h->h_mask.data(), h->h_mask.size(), cudaMemcpyHostToDevice, h->stream));
     if (h->n_ring) {
         CU(h, cudaMalloc(&h->d_ring, sizeof(int2) * ring.size()));
@@ -422,6 +461,8 @@ P2pArgs p2p_args(lbm_handle h, int dst_index, int seq) {
     x.east_flag = h->east >= 0 ? h->peer_flags[1] + 0 : nullptr;
     x.blocks_done = h->d_blocks_done;
     x.seq = seq;
+    x.status = h->d_status;
+    x.timeout_ns = h->halo_timeout_ns;
     return x;
 }
 
@@ -449,7 +490,7 @@ int slab_barrier(lbm_handle h) {
 // Exchange CUDA IPC handles of both population buffers and the flag words with the x-neighbours
 // and map theirs.  Any failure on any rank leaves every rank on the NCCL path.
 int setup_p2p(lbm_handle h) {
-    struct Pack { cudaIpcMemHandle_t f0, f1, flags; };
+    struct Pack { cudaIpcMemHandle_t f0, f1, flags; char uuid[16]; };
     const NcclApi& N = nccl_api();
     bool ok = true;
     if (const char* v = std::getenv("LBM_B200_P2P")) ok = std::atoi(v) != 0;
@@ -458,26 +499,45 @@ int setup_p2p(lbm_handle h) {
         return fail(h, LBM_ERR_NOMEM, "cudaMalloc of the halo flags failed");
     CU(h, cudaMemsetAsync(h->d_flags, 0, 64 * sizeof(int), h->stream));
     CU(h, cudaMemsetAsync(h->d_blocks_done, 0, sizeof(unsigned int), h->stream));
+    if (cudaMalloc(&h->d_status, sizeof(int)) != cudaSuccess) return fail(h, LBM_ERR_NOMEM, "cudaMalloc of the halo status word failed");
+    CU(h, cudaMemsetAsync(h->d_status, 0, sizeof(int), h->stream));
+    {
+        cudaDeviceProp prop;
+        CU(h, cudaGetDeviceProperties(&prop, h->device));
+        std::memcpy(mine.uuid, prop.uuid.bytes, 16);
+    }
     ok = ok && cudaIpcGetMemHandle(&mine.f0, h->f[0]) == cudaSuccess && cudaIpcGetMemHandle(&mine.f1, h->f[1]) == cudaSuccess &&
          cudaIpcGetMemHandle(&mine.flags, h->d_flags) == cudaSuccess;
     cudaGetLastError();
     Pack* d_io = nullptr;  // [0] mine, [1] from west, [2] from east
     CU(h, cudaMalloc(&d_io, 3 * sizeof(Pack)));
-    CU(h, cudaMemcpyAsync(d_io, &mine, sizeof(Pack), cudaMemcpyHostToDevice, h->stream));
-    NC(h, N.GroupStart());
-    if (h->east >= 0) {
-        NC(h, N.Send(d_io, sizeof(Pack), ncclChar, h->east, h->comm, h->stream));
-        NC(h, N.Recv(d_io + 2, sizeof(Pack), ncclChar, h->east, h->comm, h->stream));
-    }
-    if (h->west >= 0) {
-        NC(h, N.Send(d_io, sizeof(Pack), ncclChar, h->west, h->comm, h->stream));
-        NC(h, N.Recv(d_io + 1, sizeof(Pack), ncclChar, h->west, h->comm, h->stream));
-    }
-    NC(h, N.GroupEnd());
     Pack got[3];
-    CU(h, cudaMemcpyAsync(got, d_io, 3 * sizeof(Pack), cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaStreamSynchronize(h->stream));
-    cudaFree(d_io);
+    {
+        // (a lambda so that every early return below frees d_io)
+        auto swap_packs = [&]() -> int {
+            CU(h, cudaMemcpyAsync(d_io, &mine, sizeof(Pack), cudaMemcpyHostToDevice, h->stream));
+            NC(h, N.GroupStart());
+            if (h->east >= 0) {
+                NC(h, N.Send(d_io, sizeof(Pack), ncclChar, h->east, h->comm, h->stream));
+                NC(h, N.Recv(d_io + 2, sizeof(Pack), ncclChar, h->east, h->comm, h->stream));
+            }
+            if (h->west >= 0) {
+                NC(h, N.Send(d_io, sizeof(Pack), ncclChar, h->west, h->comm, h->stream));
+                NC(h, N.Recv(d_io + 1, sizeof(Pack), ncclChar, h->west, h->comm, h->stream));
+            }
+            NC(h, N.GroupEnd());
+            CU(h, cudaMemcpyAsync(got, d_io, 3 * sizeof(Pack), cudaMemcpyDeviceToHost, h->stream));
+            CU(h, cudaStreamSynchronize(h->stream));
+            return LBM_OK;
+        };
+        const int rc = swap_packs();
+        cudaFree(d_io);
+        if (rc) return rc;
+    }
+    // Two slabs on ONE GPU would have their step kernels wait for each other inside the same device: progress
+    // would hang on time-slicing between processes.  Such a job exchanges by NCCL.
+    for (int side = 0; side < 2; ++side)
+        if ((side == 0 ? h->west : h->east) >= 0 && std::memcmp(got[1 + side].uuid, mine.uuid, 16) == 0) ok = false;
     for (int side = 0; side < 2 && ok; ++side) {
         if ((side == 0 ? h->west : h->east) < 0) continue;
         const Pack& p = got[1 + side];
@@ -560,7 +620,8 @@ int step_one_aa(lbm_handle h) {
         h->bulk_events.push_back(e0);
         h->bulk_events.push_back(e1);
         h->bulk_timed_launches += 1;
-        h->bulk_timed_cells += (long long)(a.x_end - a.x_begin) * (L.ny - (a.skip_rows ? 2 : 0));
+        h->bulk_timed_cells += (long long)(a.x_end - a.x_begin) * (L.ny - (a.skip_rows ? 2 : 0)) - h->n_deep;
+        h->bulk_timed_updates += (long long)(a.x_end - a.x_begin) * (L.ny - (a.skip_rows ? 2 : 0)) - h->n_deep;
     } else {
         CU(h, launch_aa_bulk(odd, a, h->stream));
     }
@@ -601,6 +662,169 @@ int step_one_aa(lbm_handle h) {
     return LBM_OK;
 }
 
+
+// ---- temporal blocking (variant BULK_TB) ---------------------------------------------------------
+bool multi_slab(lbm_handle h) { return h->west >= 0 || h->east >= 0; }
+
+// Ghost columns a slab interface keeps current: the deepest pass of the job.
+int halo_width(lbm_handle h) { return h->tb_depth < 2 ? 2 : h->tb_depth; }
+
+TbArgs tb_args(lbm_handle h, const double* src, double* dst, int bad_iter, int write) {
+    TbArgs a{};
+    a.src = src;
+    a.dst = dst;
+    a.L = h->L;
+    a.tau_inv = 1.0 / h->p.tau;  // include/LBMSolver.h:85
+    a.Fx = h->p.body_force_x;
+    a.Fy = h->p.body_force_y;
+    a.first_bad = h->d_first_bad;
+    a.bad_iter = bad_iter;
+    a.bc = h->bc;
+    a.mask = h->d_mask;
+    a.mask_lo = h->mask_lo;
+    a.mask_hi = h->mask_hi;
+    a.west = h->west >= 0 ? TB_EDGE_HALO : (h->periodic_x ? TB_EDGE_WRAP : TB_EDGE_CONST);
+    a.east = h->east >= 0 ? TB_EDGE_HALO : (h->periodic_x ? TB_EDGE_WRAP : TB_EDGE_CONST);
+    a.periodic_y = h->periodic_y ? 1 : 0;
+    a.pull = 1;
+    a.write = write;
+    a.halo_w = halo_width(h);
+    return a;
+}
+
+int ensure_native_macros(lbm_handle h) {
+    if (h->d_mrho) return LBM_OK;
+    const size_t n = (size_t)h->L.lnx * h->L.ny * sizeof(double);
+    CU(h, cudaMalloc(&h->d_mrho, n));
+    CU(h, cudaMalloc(&h->d_mux, n));
+    CU(h, cudaMalloc(&h->d_muy, n));
+    return LBM_OK;
+}
+
+// The wide halo of a pass by NCCL (the fallback where CUDA IPC is unavailable): column lnx-1-d -> the east
+// neighbour's ghost column gx = -d and column d -> the west neighbour's gx = lnx+1+d, the same populations the
+// fused kernel stores (lbm_tb.cuh).  In stream order, after the kernel; the fallback does not overlap.
+int exchange_wide(lbm_handle h, double* buf, cudaStream_t s) {
+    if (!multi_slab(h)) return LBM_OK;
+    const NcclApi& N = nccl_api();
+    const Layout& L = h->L;
+    static const int east_going[3] = {1, 5, 8}, still[3] = {0, 2, 4}, west_going[3] = {3, 6, 7};
+    const int W = halo_width(h);
+    NC(h, N.GroupStart());
+    for (int d = 0; d < W; ++d)
+        for (int g = 0; g < 3; ++g) {
+            if (g == 1 && d > W - 2) continue;
+            if (g == 2 && d > W - 3) continue;
+            // group 0: the populations moving towards the receiver; 1: staying in the column; 2: moving away
+            const int* to_e = g == 0 ? east_going : (g == 1 ? still : west_going);
+            const int* to_w = g == 0 ? west_going : (g == 1 ? still : east_going);
+            for (int k = 0; k < 3; ++k) {
+                // issue order send-east, recv-west, send-west, recv-east: see exchange()
+                if (h->east >= 0) NC(h, N.Send(buf + to_e[k] * L.plane + L.at(L.lnx - d, 0), L.ny, ncclDouble, h->east, h->comm, s));
+                if (h->west >= 0) NC(h, N.Recv(buf + to_e[k] * L.plane + L.at(-d, 0), L.ny, ncclDouble, h->west, h->comm, s));
+                if (h->west >= 0) NC(h, N.Send(buf + to_w[k] * L.plane + L.at(1 + d, 0), L.ny, ncclDouble, h->west, h->comm, s));
+                if (h->east >= 0) NC(h, N.Recv(buf + to_w[k] * L.plane + L.at(L.lnx + 1 + d, 0), L.ny, ncclDouble, h->east, h->comm, s));
+            }
+        }
+    NC(h, N.GroupEnd());
+    return LBM_OK;
+}
+
+void record_bulk(lbm_handle h, cudaEvent_t e0, cudaEvent_t e1, long long cells, int depth) {
+    h->bulk_events.push_back(e0);
+    h->bulk_events.push_back(e1);
+    h->bulk_timed_launches += 1;
+    h->bulk_timed_cells += cells;
+    h->bulk_timed_updates += cells * depth;
+}
+
+// `depth` reference iterations (include/LBMSolver.h:49-58) in ONE launch and one pass over HBM.
+int step_tb(lbm_handle h, int depth, bool emit) {
+    const Layout& L = h->L;
+    const bool pull = h->cur_is_next;
+    if (!pull && depth != 1) return fail(h, LBM_ERR_INVALID, "internal: the first iteration is a pass of depth 1");
+    double* dst = h->f[h->cur ^ 1];
+    TbArgs a = tb_args(h, h->f[h->cur], dst, h->iter - 1, 1);
+    a.pull = pull ? 1 : 0;
+    if (emit) {
+        int rc = ensure_native_macros(h);
+        if (rc) return rc;
+        a.m_rho = h->d_mrho;
+        a.m_ux = h->d_mux;
+        a.m_uy = h->d_muy;
+    }
+    const bool multi = multi_slab(h);
+    const bool fused = multi && h->p2p;
+    if (fused) {
+        h->edge_seq += 1;
+        a.px = p2p_args(h, h->cur ^ 1, h->edge_seq);
+    }
+    if (h->time_bulk && (h->iter % h->time_bulk) < depth) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, h->stream);
+        CU(h, launch_tb(depth, a, fused, h->stream));
+        cudaEventRecord(e1, h->stream);
+        record_bulk(h, e0, e1, (long long)L.lnx * L.ny - h->n_deep, depth);
+    } else {
+        CU(h, launch_tb(depth, a, fused, h->stream));
+    }
+    h->launches += 1;
+    if (multi && !fused) {
+        int rc = exchange_wide(h, dst, h->stream);
+        if (rc) return rc;
+    }
+    if (!pull && h->n_solid) {
+        // The buffer just read may hold anything in its solid cells (an uploaded f_current); it is the
+        // next destination and solid cells are never stored: give them w once, now.
+        StepArgs back = step_args(h, h->f[h->cur], h->f[h->cur], h->iter - 1, 1);
+        CU(h, launch_fixup(false, back, h->bc, nullptr, 0, h->d_solids, h->n_solid, h->stream));
+        h->launches += 1;
+    }
+    // The passes themselves address periodic edges by wrapped indices; the ghost copies are for the observers.
+    if (h->periodic_x && h->world == 1) { CU(h, launch_wrap(dst, L, 1, 0, h->stream)); h->launches += 1; }
+    if (h->periodic_y) {
+        if (fused) {
+            int rc = join_halo(h);
+            if (rc) return rc;
+        }
+        CU(h, launch_wrap(dst, L, 0, 1, h->stream));
+        h->launches += 1;
+    }
+    const int last = h->iter + depth - 1;  // the collision whose populations dst holds
+    if (h->p.output_frequency > 0 && last % h->p.output_frequency == 0) {  // IOManager::record_forces, LBMSolver.h:52-54
+        if ((int)h->pending.size() >= FORCE_SLOTS) {
+            int rc = drain_forces(h);
+            if (rc) return rc;
+        }
+        const int slot = (int)h->pending.size();
+        CU(h, launch_forces(dst, h->d_links, h->n_links, h->d_forces + 2 * slot, h->stream));
+        h->launches += 1;
+        h->pending.push_back({last, slot});
+    }
+    h->cur ^= 1;
+    h->prev_is_next = depth > 1 ? true : h->cur_is_next;
+    h->cur_is_next = true;
+    h->lag = depth;
+    h->fresh = false;
+    h->macros_valid = false;
+    h->iter += depth;
+    if (emit) h->macros_native_iter = h->iter;
+    return LBM_OK;
+}
+
+// How many iterations the next pass covers: as deep as the job allows, but an iteration whose collision is an
+// output step (forces are taken from ITS populations) must be the last one of its pass, and the first
+// iteration after initialise / upload stands alone.
+int next_depth(lbm_handle h, int remaining) {
+    if (!h->cur_is_next) return 1;
+    int d = 1;
+    const int of = h->p.output_frequency;
+    while (d < h->tb_depth && d < remaining && !(of > 0 && (h->iter + d - 1) % of == 0)) ++d;
+    return d;
+}
+
 // One reference iteration (include/LBMSolver.h:49-58) as kernel launches.
 int step_one(lbm_handle h) {
     if (h->aa) return step_one_aa(h);
@@ -622,7 +846,8 @@ int step_one(lbm_handle h) {
             h->bulk_events.push_back(e0);
             h->bulk_events.push_back(e1);
             h->bulk_timed_launches += 1;
-            h->bulk_timed_cells += (long long)(x1 - x0) * L.ny;
+            h->bulk_timed_cells += (long long)(x1 - x0) * L.ny - h->n_deep;  // deep obstacle cells are skipped
+            h->bulk_timed_updates += (long long)(x1 - x0) * L.ny - h->n_deep;
             return r;
         }
         return launch_bulk(h->variant, pull, a, h->stream, x0, x1);
@@ -653,7 +878,8 @@ int step_one(lbm_handle h) {
                 h->bulk_events.push_back(e0);
                 h->bulk_events.push_back(e1);
                 h->bulk_timed_launches += 1;
-                h->bulk_timed_cells += (long long)L.lnx * L.ny;
+                h->bulk_timed_cells += (long long)L.lnx * L.ny - h->n_deep;
+                h->bulk_timed_updates += (long long)L.lnx * L.ny - h->n_deep;
             } else {
                 CU(h, launch_bulk_p2p(pull, a, h->bc, h->d_mask, px, h->stream));
             }
@@ -722,6 +948,7 @@ int step_one(lbm_handle h) {
     h->cur ^= 1;
     h->prev_is_next = h->cur_is_next;
     h->cur_is_next = true;
+    h->lag = 1;
     h->fresh = false;
     h->macros_valid = false;
     h->iter += 1;
@@ -738,12 +965,42 @@ int ensure_macros(lbm_handle h) {
     }
     if (h->snapshot_pending) CU(h, cudaStreamWaitEvent(h->stream, h->ev_snapshot, 0));
     { int rc_ = join_halo(h); if (rc_) return rc_; }
-    if (h->aa)
+    if (h->aa) {
         CU(h, launch_aa_macros(aa_observe(h), h->d_rho, h->d_ux, h->d_uy, h->stream));
-    else
+        h->launches += 1;
+        h->macros_valid = true;
+        return LBM_OK;
+    }
+    bool read_prev = false;  // the kernels below pull from the PREVIOUS buffer, ghost columns included
+    if (h->macros_native_iter != h->iter && h->cur_is_next && h->lag > 1) {
+        // The last pass covered several iterations and did not emit: its source buffer is still intact, so the
+        // same pass once more, storing no population, emits the moments its last collision read.
+        int rc = ensure_native_macros(h);
+        if (rc) return rc;
+        TbArgs a = tb_args(h, h->f[h->cur ^ 1], h->f[h->cur], h->iter - h->lag - 1, 0);
+        a.first_bad = h->d_first_bad_all;  // (already judged by the pass itself; keep the verdict word untouched)
+        a.m_rho = h->d_mrho;
+        a.m_ux = h->d_mux;
+        a.m_uy = h->d_muy;
+        CU(h, launch_tb(h->lag, a, false, h->stream));
+        h->launches += 1;
+        h->macros_native_iter = h->iter;
+        read_prev = true;
+    }
+    if (h->macros_native_iter == h->iter && h->cur_is_next) {
+        CU(h, launch_macros_finish(observe_args(h), h->d_mrho, h->d_mux, h->d_muy, h->d_rho, h->d_ux, h->d_uy, h->stream));
+    } else {
         CU(h, launch_macros(observe_args(h), h->d_rho, h->d_ux, h->d_uy, h->stream));
+        read_prev = h->cur_is_next && h->prev_is_next;
+    }
     h->launches += 1;
     h->macros_valid = true;
+    if (read_prev && h->p2p && multi_slab(h)) {
+        // A neighbour may start its next pass as soon as it has MY halo of the last one, and that pass stores
+        // into the ghost columns of the buffer just read.  Nobody moves on before every slab has observed:
+        // in a multi-slab job the observers of rho / u are collective calls (include/lbm_b200.h).
+        return slab_barrier(h);
+    }
     return LBM_OK;
 }
 
@@ -764,10 +1021,31 @@ int check_pending(lbm_handle h) {
         return LBM_OK;
     }
     { int rc_ = join_halo(h); if (rc_) return rc_; }
+    if (h->variant == BULK_TB) {
+        TbArgs t = tb_args(h, h->f[h->cur], h->f[h->cur ^ 1], h->iter - 1, 0);
+        CU(h, launch_tb(1, t, false, h->stream));
+        h->launches += 1;
+        return LBM_OK;
+    }
     StepArgs a = step_args(h, h->f[h->cur], h->f[h->cur ^ 1], h->iter - 1, 0);
     CU(h, launch_bulk(BULK_VEC2, true, a, h->stream, 0, h->L.lnx));
     CU(h, launch_fixup(true, a, h->bc, h->d_ring, h->n_ring, nullptr, 0, h->stream));
     h->launches += 2;
+    return LBM_OK;
+}
+
+// A halo wait that ran into its bound (lbm_device.cuh) leaves a mark in the slab's status word: from then on
+// the results are void and every synchronising entry point says so instead of hanging.
+int halo_status(lbm_handle h) {
+    if (!h->d_status) return LBM_OK;
+    if (!h->halo_failed) {
+        int st = 0;
+        CU(h, cudaMemcpyAsync(&st, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        h->halo_failed = st != 0;
+    }
+    if (h->halo_failed)
+        return fail(h, LBM_ERR_NCCL, "halo exchange timed out: a neighbouring slab stopped delivering (LBM_B200_HALO_TIMEOUT_MS)");
     return LBM_OK;
 }
 
@@ -777,6 +1055,7 @@ int read_first_bad(lbm_handle h, int* out) {
     int v = INT_MAX;
     const int* src = h->d_first_bad;
     { int rc_ = join_halo(h); if (rc_) return rc_; }  // edge kernels flag too
+    { int rc_ = halo_status(h); if (rc_) return rc_; }  // (before the collective: a lost neighbour would never join it)
     if (h->comm) {
         NC(h, nccl_api().AllReduce(h->d_first_bad, h->d_first_bad_all, 1, ncclInt, ncclMin, h->comm, h->stream));
         src = h->d_first_bad_all;
@@ -784,7 +1063,7 @@ int read_first_bad(lbm_handle h, int* out) {
     CU(h, cudaMemcpyAsync(&v, src, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     *out = v;
-    return LBM_OK;
+    return halo_status(h);
 }
 
 int create_common(const lbm_params* p, int device, int rank, int world, const void* uid, lbm_handle* out) {
@@ -832,6 +1111,9 @@ int create_common(const lbm_params* p, int device, int rank, int world, const vo
     if (const char* v = std::getenv("LBM_B200_VARIANT")) h->variant = std::atoi(v);
     if (const char* v = std::getenv("LBM_B200_OVERLAP")) h->overlap = std::atoi(v) != 0;
     if (const char* v = std::getenv("LBM_B200_COLSKIP")) h->col_skip = std::atoi(v) != 0;
+    if (const char* v = std::getenv("LBM_B200_TB_DEPTH")) h->tb_depth = std::min(std::max(std::atoi(v), 1), (int)TB_MAX_DEPTH);
+    if (const char* v = std::getenv("LBM_B200_HALO_TIMEOUT_MS")) h->halo_timeout_ns = (unsigned long long)std::atoll(v) * 1000000ull;
+    if (h->variant < 0 || h->variant > BULK_TB) h->variant = BULK_TB;
     if (world > 1) {
         h->west = rank > 0 ? rank - 1 : (h->periodic_x ? world - 1 : -1);
         h->east = rank < world - 1 ? rank + 1 : (h->periodic_x ? 0 : -1);
@@ -958,7 +1240,7 @@ int lbm_destroy(lbm_handle h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
-    if (h->comm && h->p2p) slab_barrier(h);  // no neighbour may still be storing into this slab's memory
+    if (h->comm && h->p2p && !h->halo_failed) slab_barrier(h);  // no neighbour may still be storing into this slab's memory
     close_p2p(h);
     if (h->comm) nccl_api().CommDestroy(h->comm);
     for (cudaEvent_t e : h->bulk_events) cudaEventDestroy(e);
@@ -970,7 +1252,8 @@ int lbm_destroy(lbm_handle h) {
     cudaFree(h->d_links); cudaFree(h->d_rho); cudaFree(h->d_ux); cudaFree(h->d_uy); cudaFree(h->d_scratch);
     cudaFree(h->d_first_bad); cudaFree(h->d_forces); cudaFree(h->d_maxbits);
     cudaFree(h->d_red); cudaFree(h->d_gather); cudaFree(h->d_first_bad_all);
-    cudaFree(h->d_flags); cudaFree(h->d_blocks_done);
+    cudaFree(h->d_flags); cudaFree(h->d_blocks_done); cudaFree(h->d_status);
+    cudaFree(h->d_mrho); cudaFree(h->d_mux); cudaFree(h->d_muy);
     cudaFree(h->d_cols); cudaFree(h->d_fills); cudaFree(h->d_links_rev); cudaFree(h->d_links_nat); cudaFree(h->d_ring_out);
     if (h->ev_macros) cudaEventDestroy(h->ev_macros);
     if (h->ev_snapshot) cudaEventDestroy(h->ev_snapshot);
@@ -999,6 +1282,8 @@ int lbm_get_info(lbm_handle h, lbm_info* o) {
     o->row_pitch = h->L.PY;
     o->kernel_variant = h->variant;
     o->halo_p2p = h->p2p ? 1 : 0;
+    o->pass_depth = (h->variant == BULK_TB && !h->aa) ? h->tb_depth : 1;
+    o->deep_solid_cells = (int32_t)h->n_deep;
     return LBM_OK;
 }
 
@@ -1042,6 +1327,8 @@ int lbm_initialise(lbm_handle h, double inlet_u) {
     h->initialised = true;
     h->iter = 0;
     h->macros_valid = false;
+    h->lag = 1;
+    h->macros_native_iter = -1;
     h->pending.clear();
     h->force_log.clear();
     if (h->p2p) return slab_barrier(h);  // every slab initialised before any neighbour pushes a halo into it
@@ -1053,9 +1340,23 @@ int lbm_step(lbm_handle h, int n_steps) {
     if (!h->initialised) return fail(h, LBM_ERR_INVALID, "lbm_initialise or lbm_upload_f first");
     if (n_steps < 0) return fail(h, LBM_ERR_INVALID, "n_steps < 0");
     CU(h, cudaSetDevice(h->device));
-    for (int k = 0; k < n_steps; ++k) {
-        int rc = step_one(h);
+    if (h->halo_failed) return halo_status(h);
+    if (h->aa || h->variant != BULK_TB) {
+        for (int k = 0; k < n_steps; ++k) {
+            int rc = step_one(h);
+            if (rc) return rc;
+        }
+        return LBM_OK;
+    }
+    for (int k = 0; k < n_steps;) {
+        const int d = next_depth(h, n_steps - k);
+        const int last = h->iter + d - 1, of = h->p.output_frequency;
+        // Solver::run looks at rho / u after every output step (max_velocity, VTK), lbm_run's caller after the
+        // call: those passes emit the moments of their last collision (24 B per cell, once per output period)
+        const bool emit = (of > 0 && last > 0 && last % of == 0) || (h->emit_last && k + d == n_steps);
+        int rc = step_tb(h, d, emit);
         if (rc) return rc;
+        k += d;
     }
     return LBM_OK;
 }
@@ -1066,7 +1367,7 @@ int lbm_sync(lbm_handle h) {
     CU(h, cudaStreamSynchronize(h->stream));
     CU(h, cudaStreamSynchronize(h->comm_stream));
     CU(h, cudaStreamSynchronize(h->copy_stream));
-    return LBM_OK;
+    return halo_status(h);
 }
 
 int lbm_run(lbm_handle h, int n_steps, double* rows, int max_rows, int* n_rows, int* unstable_at) {
@@ -1078,11 +1379,21 @@ int lbm_run(lbm_handle h, int n_steps, double* rows, int max_rows, int* n_rows, 
     int bad = INT_MAX;
     // Launch in chunks; look at the stability flag between chunks so that a blown-up run stops
     // within one chunk instead of grinding through NaNs for 120 000 steps.
-    const int chunk = h->p.output_frequency > 0 ? (h->p.output_frequency < 64 ? 64 : h->p.output_frequency) : 256;
+    // Chunks END on output steps (as Solver::run's do), so that a temporally blocked pass never has to be cut
+    // short in the middle of a chunk: an output iteration is the last one of its pass anyway.
+    const int of = h->p.output_frequency;
     int done = 0;
     while (done < n_steps) {
-        const int n = (n_steps - done < chunk) ? (n_steps - done) : chunk;
+        int n = 256;
+        if (of > 0) {
+            int end = ((h->iter + of - 1) / of) * of;  // the next output iteration (possibly this one) ...
+            while (end - h->iter + 1 < 64) end += of;  // ... but at least 64 iterations between two looks at the flags
+            n = end - h->iter + 1;
+        }
+        if (n > n_steps - done) n = n_steps - done;
+        h->emit_last = (done + n == n_steps);
         int rc = lbm_step(h, n);
+        h->emit_last = false;
         if (rc) return rc;
         done += n;
         rc = drain_forces(h);
@@ -1202,7 +1513,7 @@ int lbm_download_solid(lbm_handle h, unsigned char* mask) {
     CHECK_H(h);
     if (!mask) return fail(h, LBM_ERR_INVALID, "null mask");
     for (int y = 0; y < h->L.ny; ++y)
-        for (int x = 0; x < h->L.lnx; ++x) mask[(size_t)y * h->L.lnx + x] = h->h_mask[h->L.at(x + 1, y)];
+        for (int x = 0; x < h->L.lnx; ++x) mask[(size_t)y * h->L.lnx + x] = h->h_mask[h->L.at(x + 1, y)] ? 1 : 0;
     return LBM_OK;
 }
 
@@ -1243,6 +1554,8 @@ int lbm_upload_f(lbm_handle h, const double* aos, int iteration) {
     h->initialised = true;
     h->iter = iteration;
     h->macros_valid = false;
+    h->lag = 1;
+    h->macros_native_iter = -1;
     if (h->p2p) return slab_barrier(h);
     return LBM_OK;
 }
@@ -1314,7 +1627,7 @@ int lbm_time_steps(lbm_handle h, int n_steps, int per_kernel, float* ms_total, f
     CU(h, cudaEventCreate(&e1));
     const long long l0 = h->launches;
     h->time_bulk = per_kernel > 0 ? per_kernel : 0;
-    if (h->time_bulk) h->bulk_timed_launches = h->bulk_timed_cells = 0;
+    if (h->time_bulk) h->bulk_timed_launches = h->bulk_timed_cells = h->bulk_timed_updates = 0;
     CU(h, cudaStreamSynchronize(h->comm_stream));
     CU(h, cudaStreamSynchronize(h->stream));
     CU(h, cudaEventRecord(e0, h->stream));
@@ -1348,6 +1661,21 @@ int lbm_get_counters(lbm_handle h, long long* launches, long long* bulk_launches
     if (launches) *launches = h->launches;
     if (bulk_launches) *bulk_launches = h->bulk_timed_launches;
     if (bulk_cells) *bulk_cells = h->bulk_timed_cells;
+    return LBM_OK;
+}
+
+int lbm_get_bulk_updates(lbm_handle h, long long* updates) {
+    CHECK_H(h);
+    if (updates) *updates = h->bulk_timed_updates;
+    return LBM_OK;
+}
+
+int lbm_set_pass_depth(lbm_handle h, int depth) {
+    CHECK_H(h);
+    if (depth < 1 || depth > TB_MAX_DEPTH) return fail(h, LBM_ERR_INVALID, "pass depth must be 1, 2 or 3");
+    if (depth != h->tb_depth && multi_slab(h) && h->initialised && h->cur_is_next)
+        return fail(h, LBM_ERR_INVALID, "in a multi-slab job the pass depth can only change before the first iteration");
+    h->tb_depth = depth;
     return LBM_OK;
 }
 
@@ -1491,7 +1819,10 @@ int lbm_gather_macros(lbm_handle h, double* rho, double* ux, double* uy) {
 
 int lbm_set_kernel_variant(lbm_handle h, int variant) {
     CHECK_H(h);
-    if (variant < 0 || variant > 1) return fail(h, LBM_ERR_INVALID, "variant must be 0 or 1");
+    if (variant < 0 || variant > BULK_TB) return fail(h, LBM_ERR_INVALID, "variant must be 0, 1 or 2");
+    if (variant != h->variant && multi_slab(h) && h->initialised && h->cur_is_next)
+        return fail(h, LBM_ERR_INVALID, "in a multi-slab job the kernel variant can only change before the first iteration "
+                                        "(the temporally blocked passes keep a wider halo current)");
     h->variant = variant;
     return LBM_OK;
 }

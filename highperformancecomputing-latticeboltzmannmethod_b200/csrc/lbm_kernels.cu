@@ -12,54 +12,13 @@
 #include <cstdint>
 
 #include "lbm_cell.cuh"
+#include "lbm_device.cuh"
 #include "lbm_kernels.cuh"
 #include "lbm_launch.cuh"
 
 namespace lbm {
 
 namespace {
-
-template <bool PULL>
-__device__ __forceinline__ void load_cell(const double* __restrict__ src, const Layout& L, int gx, int y,
-                                          double f[Q]) {
-#pragma unroll
-    for (int i = 0; i < Q; ++i) {
-        const int dx = PULL ? cxi(i) : 0, dy = PULL ? cyi(i) : 0;
-        f[i] = __ldg(src + i * L.plane + L.at(gx - dx, y - dy));
-    }
-}
-
-__device__ __forceinline__ void store_cell(double* __restrict__ dst, const Layout& L, int gx, int y,
-                                           const double f[Q]) {
-#pragma unroll
-    for (int i = 0; i < Q; ++i) dst[i * L.plane + L.at(gx, y)] = f[i];
-}
-
-template <bool FORCED>
-__device__ __forceinline__ void collide_cell(double f[Q], double tau_inv, double Fx, double Fy) {
-    const Moments m = moments(f);
-    if (FORCED)
-        bgk_forced(f, m, tau_inv, Fx, Fy, f);
-    else
-        bgk(f, m, tau_inv, f);
-}
-
-__device__ __forceinline__ bool any_unstable(const double f[Q]) {
-    bool bad = false;
-#pragma unroll
-    for (int i = 0; i < Q; ++i) bad |= unstable_value(f[i]);
-    return bad;
-}
-
-// The reference's boundary rules in its serial order (include/LBMSolver.h:153-236):
-// bottom row, top row, inlet column, outlet column.  x, y are slab-interior coordinates.
-__device__ __forceinline__ void apply_bc(double f[Q], int x, int y, const Layout& L, const BcArgs& b,
-                                         double& rho_bc, double& u_out) {
-    if (b.walls && y == 0) wall_bottom(f);
-    if (b.walls && y == L.ny - 1) wall_top(f);
-    if (b.inlet && x == 0) rho_bc = zou_he_inlet(f, b.u_in);
-    if (b.outlet && x == L.lnx - 1) u_out = zou_he_outlet(f);
-}
 
 // ------------------------------------------------------------------------------------------
 // Bulk kernel, variant 0: one cell per thread.  Correct for any ny; the baseline the other
@@ -210,34 +169,6 @@ __global__ void __launch_bounds__(128) k_edge(StepArgs a, BcArgs b, const unsign
 // No rank can run more than one exchange ahead of a neighbour, there is no cycle in the waits (launch
 // seq of one GPU only waits for launch seq-1 of another), and a spinning block never keeps another
 // GPU from making progress.
-__device__ __forceinline__ void spin_until(const int* flag, int want) {
-    while (*reinterpret_cast<const volatile int*>(flag) < want) __nanosleep(64);
-}
-
-// Steps 1 and 3 of the protocol for one block of edge work.
-__device__ __forceinline__ void p2p_block_begin(const P2pArgs& x) {
-    if (threadIdx.x == 0) {
-        if (x.peer_dst_west) spin_until(x.my_flags + 0, x.seq - 1);
-        if (x.peer_dst_east) spin_until(x.my_flags + 1, x.seq - 1);
-        __threadfence_system();
-    }
-    __syncthreads();
-}
-
-__device__ __forceinline__ void p2p_block_end(const P2pArgs& x, unsigned int edge_blocks) {
-    __threadfence_system();  // this block's peer stores first
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (atomicAdd(x.blocks_done, 1u) == edge_blocks - 1) {
-            *x.blocks_done = 0;
-            __threadfence_system();
-            if (x.west_flag) *reinterpret_cast<volatile int*>(x.west_flag) = x.seq;
-            if (x.east_flag) *reinterpret_cast<volatile int*>(x.east_flag) = x.seq;
-            __threadfence_system();
-        }
-    }
-}
-
 // Step 2 for one cell of edge column `col`.
 __device__ __forceinline__ void p2p_edge_cell(const StepArgs& a, const BcArgs& b, const unsigned char* __restrict__ mask, int pull,
                                               const P2pArgs& x, int col, int y) {
@@ -248,12 +179,14 @@ __device__ __forceinline__ void p2p_edge_cell(const StepArgs& a, const BcArgs& b
         for (int i = 0; i < Q; ++i) f[i] = b.w[i];
     } else {
         if (pull) {
-            load_cell<true>(a.src, L, col + 1, y, f);
+            // the ghost column was stored by the neighbouring GPU while this kernel may already have been
+            // resident: coherent loads (lbm_device.cuh)
+            load_cell<true, true>(a.src, L, col + 1, y, f);
             double rho_bc, u_out;
             apply_bc(f, col, y, L, b, rho_bc, u_out);
             if (any_unstable(f)) atomicMin(a.first_bad, a.bad_iter);
         } else {
-            load_cell<false>(a.src, L, col + 1, y, f);
+            load_cell<false, true>(a.src, L, col + 1, y, f);
         }
         if (a.forced)
             collide_cell<true>(f, a.tau_inv, a.Fx, a.Fy);
@@ -343,8 +276,8 @@ __global__ void __launch_bounds__(128) k_fixup_p2p(StepArgs a, BcArgs b, int pul
 }
 
 __global__ void k_wait_halo(P2pArgs x) {
-    if (x.peer_dst_west) spin_until(x.my_flags + 0, x.seq);
-    if (x.peer_dst_east) spin_until(x.my_flags + 1, x.seq);
+    if (x.peer_dst_west) spin_until(x.my_flags + 0, x.seq, x);
+    if (x.peer_dst_east) spin_until(x.my_flags + 1, x.seq, x);
     __threadfence_system();
 }
 
@@ -414,13 +347,15 @@ __global__ void k_init(double* __restrict__ f0, double* __restrict__ f1, Layout 
     const int y = (int)(blockIdx.x * blockDim.x + threadIdx.x) - 1;  // -1 .. ny
     if (y > L.ny) return;
     const bool ghost_row = (y < 0 || y >= L.ny);
-    for (int gx = blockIdx.y; gx < L.lnx + 2; gx += gridDim.y) {
+    // every column of the padded slab, the XO extra ghost columns of a temporally blocked halo included
+    for (int g = blockIdx.y; g < L.lnx + 2 + 2 * Layout::XO; g += gridDim.y) {
+    const int gx = g - Layout::XO;
     const bool interior = !ghost_row && gx >= 1 && gx <= L.lnx;
     double v[Q];
     if (interior && mask[L.at(gx, y)]) {
 #pragma unroll
         for (int i = 0; i < Q; ++i) v[i] = b.w[i];
-    } else if (!ghost_row && ((gx == 0 && west_zero) || (gx == L.lnx + 1 && east_zero))) {
+    } else if (!ghost_row && ((gx <= 0 && west_zero) || (gx >= L.lnx + 1 && east_zero))) {
 #pragma unroll
         for (int i = 0; i < Q; ++i) v[i] = 0.0;
     } else if (shear_wave) {
@@ -440,29 +375,18 @@ __global__ void k_reset_ghosts(double* __restrict__ f, Layout L, BcArgs b, int w
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     double z[Q] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (t < L.ny) {
-        store_cell(f, L, 0, t, west_zero ? z : b.e);
-        store_cell(f, L, L.lnx + 1, t, east_zero ? z : b.e);
+        for (int d = 0; d <= Layout::XO; ++d) {
+            store_cell(f, L, -d, t, west_zero ? z : b.e);
+            store_cell(f, L, L.lnx + 1 + d, t, east_zero ? z : b.e);
+        }
     }
-    if (t < L.lnx + 2) {
-        store_cell(f, L, t, -1, b.e);
-        store_cell(f, L, t, L.ny, b.e);
+    if (t < L.lnx + 2 + 2 * Layout::XO) {
+        store_cell(f, L, t - Layout::XO, -1, b.e);
+        store_cell(f, L, t - Layout::XO, L.ny, b.e);
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// Observables.  f_current of the reference after its last iteration, for one interior cell,
-// given the newest post-collision buffer: pull, then boundary rules (fluid) or reversal (solid)
-// (include/LBMSolver.h:128-145, 147-265).
-__device__ __forceinline__ void current_from_next(const double* __restrict__ fnext, const Layout& L,
-                                                  const unsigned char* __restrict__ mask, const BcArgs& b, int x,
-                                                  int y, double f[Q], double& rho_bc, double& u_out) {
-    load_cell<true>(fnext, L, x + 1, y, f);
-    if (mask[L.at(x + 1, y)])
-        reverse(f);
-    else
-        apply_bc(f, x, y, L, b, rho_bc, u_out);
-}
-
 // rho, ux, uy as the reference's arrays hold them (see ObserveArgs in the header).
 __device__ __forceinline__ void macros_cell(const ObserveArgs& o, int x, int y, double& rho, double& ux,
                                             double& uy) {
@@ -705,14 +629,15 @@ cudaError_t launch_wrap(double* f, const Layout& L, int wrap_x, int wrap_y, cuda
 
 cudaError_t launch_init(double* f0, double* f1, const Layout& L, const unsigned char* mask, const BcArgs& b,
                         int west_zero, int east_zero, int shear_wave, double u0, cudaStream_t s) {
-    dim3 grid(cdiv(L.ny + 2, 256), L.lnx + 2 < 65535 ? L.lnx + 2 : 65535);
+    const int ncol = L.lnx + 2 + 2 * Layout::XO;
+    dim3 grid(cdiv(L.ny + 2, 256), ncol < 65535 ? ncol : 65535);
     k_init<<<grid, 256, 0, s>>>(f0, f1, L, mask, b, west_zero, east_zero, shear_wave, u0);
     return cudaGetLastError();
 }
 
 cudaError_t launch_reset_ghosts(double* f, const Layout& L, const BcArgs& b, int west_zero, int east_zero,
                                 cudaStream_t s) {
-    const int n = (L.ny > L.lnx + 2) ? L.ny : L.lnx + 2;
+    const int n = (L.ny > L.lnx + 2 + 2 * Layout::XO) ? L.ny : L.lnx + 2 + 2 * Layout::XO;
     k_reset_ghosts<<<cdiv(n, 256), 256, 0, s>>>(f, L, b, west_zero, east_zero);
     return cudaGetLastError();
 }

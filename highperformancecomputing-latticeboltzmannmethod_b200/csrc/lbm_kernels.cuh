@@ -35,7 +35,8 @@ struct StepArgs {
     int col_lo, col_hi;  // only columns in [col_lo, col_hi) have a table entry worth loading
 };
 
-enum BulkVariant { BULK_SCALAR = 0, BULK_VEC2 = 1 };
+// BULK_TB: the temporally blocked kernels of lbm_tb.cuh (several iterations per pass over HBM; the default).
+enum BulkVariant { BULK_SCALAR = 0, BULK_VEC2 = 1, BULK_TB = 2 };
 
 // Fused pull + collide over every interior cell, no boundary logic (reference
 // include/LBMSolver.h:84-145 minus the solid `continue`).  pull=false is the very first
@@ -63,6 +64,8 @@ struct P2pArgs {
     int* east_flag;         // -> the east neighbour's my_flags[0]
     unsigned int* blocks_done;  // last-block detection
     int seq;                    // exchange number of this launch (the same on every rank)
+    int* status;                // this slab's status word: non-zero = a halo wait timed out / the host gave up
+    unsigned long long timeout_ns;  // bound of one wait (0: unbounded)
 };
 // Interior columns AND the fused edge + halo work in one launch (vectorised variant, even ny): the
 // peer stores and the hand-shake run under the interior kernel.

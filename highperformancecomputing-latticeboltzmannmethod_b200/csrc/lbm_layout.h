@@ -8,9 +8,11 @@
 //     only the +-1 shifts in y are misaligned by one element.
 // The reference's one-cell ghost ring is kept (include/LBMGrid.h:63-64): columns gx = 0 and
 // lnx+1, rows y = -1 and ny.  A column is padded in front so that interior row y = 0 starts on a
-// 128-byte boundary, and its pitch is a multiple of 16 doubles (128 B):
+// 128-byte boundary, and its pitch is a multiple of 16 doubles (128 B).  XO further ghost columns on
+// either side (gx = -1, -2 and lnx+2, lnx+3) hold the wider halo that a temporally blocked pass of
+// depth T needs from the neighbouring slab (lbm_tb.cuh): T ghost columns per face.
 //
-//   element (i, gx, y)  ->  i*plane + gx*PY + YO + y,      gx in [0, lnx+2), y in [-1, ny]
+//   element (i, gx, y)  ->  i*plane + (gx+XO)*PY + YO + y,      gx in [-XO, lnx+2+XO), y in [-1, ny]
 //
 // The reference's AoS order (include/LBMGrid.h:105-107) only exists at the API boundary
 // (lbm_download_f / lbm_upload_f), produced by a transpose kernel.
@@ -32,12 +34,13 @@ struct Layout {
     int gnx;      // global nx
     int x_start;  // global x of interior column 0
     int PY;       // column pitch, doubles
-    long long plane;  // doubles per population plane = (lnx+2)*PY
+    long long plane;  // doubles per population plane = (lnx+2+2*XO)*PY
 
     static constexpr int YO = 16;  // interior row 0 sits at this offset inside a column
+    static constexpr int XO = 2;   // extra ghost columns per side beyond the reference's one
 
-    LBM_LAYOUT_HD long long at(int gx, int y) const { return (long long)gx * PY + YO + y; }
-    LBM_LAYOUT_HD long long cells_padded() const { return (long long)(lnx + 2) * PY; }
+    LBM_LAYOUT_HD long long at(int gx, int y) const { return (long long)(gx + XO) * PY + YO + y; }
+    LBM_LAYOUT_HD long long cells_padded() const { return (long long)(lnx + 2 + 2 * XO) * PY; }
 
     static Layout make(int lnx, int ny, int gnx, int x_start) {
         Layout L;
@@ -46,7 +49,7 @@ struct Layout {
         L.gnx = gnx;
         L.x_start = x_start;
         L.PY = ((YO + ny + 1 + 15) / 16) * 16;
-        L.plane = (long long)(lnx + 2) * L.PY;
+        L.plane = (long long)(lnx + 2 + 2 * XO) * L.PY;
         return L;
     }
 };

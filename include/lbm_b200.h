@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LBM_B200_ABI_VERSION 1
+#define LBM_B200_ABI_VERSION 2
 
 typedef enum lbm_status {
     LBM_OK = 0,
@@ -83,6 +83,8 @@ typedef struct lbm_info {
     int32_t kernel_variant;
     int32_t halo_p2p;            /* 1: halo columns go by peer stores fused into the edge kernel (CUDA IPC over
                                     NVLink); 0: NCCL send/recv (or a single slab) */
+    int32_t pass_depth;          /* reference iterations per launch and per trip through HBM (temporal blocking) */
+    int32_t deep_solid_cells;    /* obstacle cells with eight solid neighbours: never loaded, computed or stored */
 } lbm_info;
 
 typedef struct lbm_solver* lbm_handle;
@@ -181,17 +183,25 @@ int lbm_time_steps(lbm_handle h, int n_steps, int per_kernel, float* ms_total, f
 /* Kernel launches issued by this handle since creation; launches and lattice cells of the bulk
  * collide-stream kernel covered by ms_bulk of the last lbm_time_steps(per_kernel=1). */
 int lbm_get_counters(lbm_handle h, long long* launches, long long* bulk_launches, long long* bulk_cells);
+/* Cell UPDATES of the launches lbm_get_counters reports (cells processed x iterations per pass): a temporally
+ * blocked launch of depth T moves each cell through HBM once and updates it T times. */
+int lbm_get_bulk_updates(lbm_handle h, long long* updates);
 /* CUDA-event marks on the handle's compute stream (after everything its side streams have in
  * flight), so that a caller can time any sequence of entry points -- uploads, runs, downloads --
  * on the device rather than by wall clock. */
 #define LBM_EVENT_SLOTS 8
 int lbm_event_record(lbm_handle h, int slot);
 int lbm_event_elapsed(lbm_handle h, int slot_a, int slot_b, float* ms);
-/* Kernel variant of the bulk kernel: 0 = one cell per thread (any ny), 1 = two y-adjacent cells
- * per thread with 128-bit loads / stores (even ny; the default, falls back to 0 for odd ny).
- * A shared-memory / TMA staged variant is deliberately absent: ncu shows DRAM traffic equal to
- * the algorithmic bytes and the kernel at the measured HBM peak. */
+/* Kernel variant of the collide-stream path:
+ *   0  one iteration per launch pair (bulk + boundary fix-up), one cell per thread, any ny;
+ *   1  the same with two y-adjacent cells per thread and 128-bit loads / stores (even ny, else 0):
+ *      at the measured HBM peak for 144 B per update;
+ *   2  (default) temporal blocking: up to lbm_set_pass_depth() iterations per launch and per trip through
+ *      HBM, intermediate states in shared memory, boundary rules inside the kernel.
+ * All three give the same bits.  In a multi-slab job the variant / depth can only change before the first
+ * iteration after lbm_initialise / lbm_upload_f. */
 int lbm_set_kernel_variant(lbm_handle h, int variant);
+int lbm_set_pass_depth(lbm_handle h, int depth); /* 1..3, default 2 (LBM_B200_TB_DEPTH) */
 int lbm_device_count(int* n);
 
 #ifdef __cplusplus

@@ -53,7 +53,7 @@ def test_initial_state_matches_grid_initialise():
 
 
 @pytest.mark.parametrize("name", list(CASES))
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_steps_match_oracle(name, variant):
     case = CASES[name]
     s, o = make_solver(case, variant), O.Oracle(case)
@@ -138,7 +138,7 @@ def test_variants_are_bit_identical_to_each_other():
     case = CASES["256x64"]
     state = util.random_state(case, 7)
     outs = []
-    for v in (0, 1):
+    for v in (0, 1, 2):
         s = make_solver(case, v)
         s.upload_f(state, 0)
         s.step(25)
