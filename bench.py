@@ -292,7 +292,7 @@ def parity_golden(n_gpus: int):
         return None
 
 
-def parity_check(lbm_b200, dist, rank, world, local_rank, nccl_id):
+def parity_check(lbm_b200, dist, rank, world, local_rank, nccl_id, variant=2, depth=None):
     """Returns the dict bench.py prints as "multi_gpu_parity" (rank 0) or None (other ranks)."""
     import numpy as np
 
@@ -300,6 +300,9 @@ def parity_check(lbm_b200, dist, rank, world, local_rank, nccl_id):
     p = lbm_b200.SimulationParams(**c)
     state = parity_state(c["nx"], c["ny"])
     s = lbm_b200.Solver(p, device=local_rank, rank=rank, world=world, nccl_id=nccl_id)
+    s.set_kernel_variant(variant)  # (a lattice this small would default to the one-iteration kernels)
+    if depth is not None:
+        s.set_pass_depth(depth)
     s.initialise()
     info = s.info()
     lnx, x0 = info.local_nx, info.x_start
@@ -317,6 +320,7 @@ def parity_check(lbm_b200, dist, rank, world, local_rank, nccl_id):
     if rank != 0:
         return None
     one = lbm_b200.Solver(p, device=local_rank)
+    one.set_kernel_variant(1)  # the reference point: one iteration per launch, the round-1 kernels
     one.initialise()
     one.upload_f(state, iteration=0)
     rows1, bad1 = one.run(PARITY_STEPS)
@@ -330,7 +334,8 @@ def parity_check(lbm_b200, dist, rank, world, local_rank, nccl_id):
     gold = parity_golden(world)
     return {"bit_identical": bool(same and all(q["bad"] == bad1 == -1 for q in parts) and
                                   np.array_equal(parts[0]["rows"][:, 0], rows1[:, 0])),
-            "against": "the same engine on one GPU (populations, f_current, rho, ux, uy: every cell)",
+            "against": "one GPU running the one-iteration kernels (populations, f_current, rho, ux, uy: every cell)",
+            "kernel_variant": int(variant),
             "forces_max_abs_diff": f_err, "forces_ok": bool(f_err <= 1e-13),
             "sha256_f_next": sha, "sha_matches_oracle": (None if gold is None else bool(sha == gold["sha256"])),
             "golden": "tests/golden/bench_parity_sha.json (CPU oracle, oracle/gen_parity_sha.py)",
@@ -462,7 +467,8 @@ def main():
     # ---- correctness first (outside every timed region): N slabs == 1 GPU == the oracle's SHA
     parity = None
     if not args.no_parity and not args.aa:
-        parity = parity_check(lbm_b200, dist, rank, world, local_rank, nccl_id)
+        parity = parity_check(lbm_b200, dist, rank, world, local_rank, nccl_id,
+                              variant=2 if args.variant is None else args.variant, depth=args.depth)
         if dist is not None:  # a fresh NCCL id for the measured job
             ident = [lbm_b200.nccl_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(ident, src=0)
@@ -497,6 +503,23 @@ def main():
     windows.append((w0, w1))
     ms = max_over_ranks(ms_total)
     ok, bad = s.check_stability()
+    physics = None
+    if args.workload == "c4" and world == 1:
+        # The shear wave u_x = u0 sin(2 pi y / ny) of the periodic obstacle-free lattice decays as exp(-nu k^2 t)
+        # (the reference has no such mode, so this analytic property is the check at FULL size):
+        # the measured decay rate against nu k^2, and the drift of the total mass.
+        n_it = s.info().iteration
+        rho_f, ux_f, uy_f = s.macros()  # the stored moments belong to f_current of iteration n_it - 1
+        kk = 2.0 * np.pi / ny
+        prof = ux_f.mean(axis=1)
+        amp = 2.0 * float((prof * np.sin(kk * np.arange(ny))).mean()) / cfg["inlet_velocity"]
+        nu = (cfg["tau"] - 0.5) / 3.0
+        rate = -np.log(amp) / max(n_it - 1, 1)
+        physics = {"iterations": int(n_it), "decay_rate_measured": float(rate), "decay_rate_nu_k2": float(nu * kk * kk),
+                   "decay_rate_rel_err": float(rate / (nu * kk * kk) - 1.0),
+                   "mass_drift": float(rho_f.sum() / (float(ny) * float(lnx)) - 1.0),
+                   "max_abs_uy": float(np.abs(uy_f).max())}
+        del rho_f, ux_f, uy_f
     value = cells_global * args.steps / (ms * 1e-3) / 1e6
     gpu_launches = s.counters()[0] - launches0
 
@@ -607,6 +630,8 @@ def main():
             "stable": bool(ok), "roofline_whole_step_frac": value * 1e6 * BYTES_PER_UPDATE / 1e9 / args.gpus / peak,
             ("multi_gpu_parity" if world > 1 else "parity_check"): parity,
         }
+        if physics is not None:
+            out["physics_check"] = physics
         emit(out)
     if dist is not None:
         dist.barrier()

@@ -106,7 +106,7 @@ EXPORTS = [
     "lbm_upload_f", "lbm_snapshot_begin", "lbm_snapshot_wait", "lbm_host_alloc", "lbm_host_free", "lbm_time_steps",
     "lbm_set_kernel_variant", "lbm_device_count", "lbm_get_counters", "lbm_event_record", "lbm_event_elapsed",
     "lbm_bootstrap_env", "lbm_set_params", "lbm_snapshot_begin_slot", "lbm_snapshot_wait_slot", "lbm_allreduce", "lbm_gather_macros",
-    "lbm_get_bulk_updates", "lbm_set_pass_depth",
+    "lbm_get_bulk_updates", "lbm_set_pass_depth", "lbm_set_force_mode",
 ]
 
 _lib = None
@@ -164,6 +164,7 @@ def load():
     L.lbm_gather_macros.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p]
     L.lbm_get_bulk_updates.argtypes = [H, LL]
     L.lbm_set_pass_depth.argtypes = [H, C.c_int]
+    L.lbm_set_force_mode.argtypes = [H, C.c_int]
     for name in EXPORTS:
         if name != "lbm_last_error":
             getattr(L, name).restype = C.c_int
@@ -371,6 +372,10 @@ class Solver:
     def set_pass_depth(self, d: int):
         """Iterations per temporally blocked pass (kernel variant 2): 1, 2 (default) or 3."""
         self._ck(load().lbm_set_pass_depth(self._h, d))
+
+    def set_force_mode(self, tree: int):
+        """0: the reference's serial summation order (its bits); 1: fixed parallel tree (a few us, equal to rounding)."""
+        self._ck(load().lbm_set_force_mode(self._h, tree))
 
     def bulk_updates(self) -> int:
         """Cell updates of the bulk launches the last time_steps(per_kernel) timed."""

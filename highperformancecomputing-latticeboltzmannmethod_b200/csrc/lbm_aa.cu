@@ -454,11 +454,11 @@ __global__ void __launch_bounds__(256) k_aa_macros(AaObserve o, double* __restri
 
 constexpr int EX_TX = 16, EX_TY = 32;
 
-__global__ void __launch_bounds__(256) k_aa_export(AaObserve o, int which, double* __restrict__ aos) {
+__global__ void __launch_bounds__(256) k_aa_export(AaObserve o, int which, double* __restrict__ aos, int row0, int rows) {
     __shared__ double t[Q][EX_TX][EX_TY + 1];
     const Layout& L = o.L;
-    const int tnx = L.lnx + 2, tny = L.ny + 2;
-    const int gx0 = blockIdx.y * EX_TX, gy0 = blockIdx.x * EX_TY;
+    const int tnx = L.lnx + 2, tny = min(L.ny + 2, row0 + rows);
+    const int gx0 = blockIdx.y * EX_TX, gy0 = row0 + blockIdx.x * EX_TY;
     for (int c = threadIdx.x; c < EX_TX * EX_TY; c += blockDim.x) {
         const int xl = c / EX_TY, yl = c % EX_TY;
         const int gx = gx0 + xl, gy = gy0 + yl;
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(256) k_aa_export(AaObserve o, int which, doubl
         const int yl = k / (nxl * Q), e = k % (nxl * Q);
         const int gy = gy0 + yl;
         if (gy >= tny) break;
-        aos[((long long)gy * tnx + gx0) * Q + e] = t[e % Q][e / Q][yl];
+        aos[((long long)(gy - row0) * tnx + gx0) * Q + e] = t[e % Q][e / Q][yl];
     }
 }
 
@@ -564,9 +564,9 @@ cudaError_t launch_aa_macros(const AaObserve& o, double* rho, double* ux, double
     return cudaGetLastError();
 }
 
-cudaError_t launch_aa_export(const AaObserve& o, int which, double* aos, cudaStream_t s) {
-    dim3 grid(cdiv(o.L.ny + 2, EX_TY), cdiv(o.L.lnx + 2, EX_TX));
-    k_aa_export<<<grid, 256, 0, s>>>(o, which, aos);
+cudaError_t launch_aa_export(const AaObserve& o, int which, double* aos, int row0, int rows, cudaStream_t s) {
+    dim3 grid(cdiv(rows, EX_TY), cdiv(o.L.lnx + 2, EX_TX));
+    k_aa_export<<<grid, 256, 0, s>>>(o, which, aos, row0, rows);
     return cudaGetLastError();
 }
 

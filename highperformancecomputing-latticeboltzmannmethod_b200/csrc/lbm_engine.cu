@@ -86,10 +86,15 @@ struct lbm_solver {
     int lag = 1;
     double *d_mrho = nullptr, *d_mux = nullptr, *d_muy = nullptr;
     int macros_native_iter = -1;
+    int force_tree = 0;      // LBM_FORCES_TREE: fixed parallel reduction tree instead of the reference's serial order
     bool emit_last = false;  // lbm_run: the last pass of the call emits (the caller will look at the fields)
     int mask_lo = 0, mask_hi = 0;  // padded columns gx in [lo, hi) hold solid cells
     long long n_deep = 0;          // interior solid cells whose eight neighbours are solid (never touched)
-    double* d_scratch = nullptr;  // padded AoS staging for lbm_download_f / lbm_upload_f
+    // lbm_download_f / lbm_upload_f: the padded AoS image crosses PCIe in row chunks through two staging buffers,
+    // the copy of one chunk overlapping the transpose kernel of the other (no full-size third buffer)
+    double* d_stage[2] = {nullptr, nullptr};
+    int stage_rows = 0;  // padded rows per chunk (a multiple of 32)
+    cudaEvent_t ev_stage_copied[2] = {nullptr, nullptr}, ev_stage_free[2] = {nullptr, nullptr};
     unsigned long long* d_maxbits = nullptr;
 
     int* d_first_bad = nullptr;
@@ -654,7 +659,7 @@ int step_one_aa(lbm_handle h) {
             if (rc) return rc;
         }
         const int slot = (int)h->pending.size();
-        CU(h, launch_forces(h->f[0], aa_links(h), h->n_links, h->d_forces + 2 * slot, h->stream));
+        CU(h, launch_forces(h->f[0], aa_links(h), h->n_links, h->d_forces + 2 * slot, h->stream, h->force_tree));
         h->launches += 1;
         h->pending.push_back({h->iter, slot});
     }
@@ -799,7 +804,7 @@ int step_tb(lbm_handle h, int depth, bool emit) {
             if (rc) return rc;
         }
         const int slot = (int)h->pending.size();
-        CU(h, launch_forces(dst, h->d_links, h->n_links, h->d_forces + 2 * slot, h->stream));
+        CU(h, launch_forces(dst, h->d_links, h->n_links, h->d_forces + 2 * slot, h->stream, h->force_tree));
         h->launches += 1;
         h->pending.push_back({last, slot});
     }
@@ -940,7 +945,7 @@ int step_one(lbm_handle h) {
             if (rc) return rc;
         }
         const int slot = (int)h->pending.size();
-        CU(h, launch_forces(dst, h->d_links, h->n_links, h->d_forces + 2 * slot, h->stream));
+        CU(h, launch_forces(dst, h->d_links, h->n_links, h->d_forces + 2 * slot, h->stream, h->force_tree));
         h->launches += 1;
         h->pending.push_back({h->iter, slot});
     }
@@ -1004,10 +1009,18 @@ int ensure_macros(lbm_handle h) {
     return LBM_OK;
 }
 
-int ensure_scratch(lbm_handle h) {
-    if (h->d_scratch) return LBM_OK;
-    const size_t n = (size_t)(h->L.lnx + 2) * (h->L.ny + 2) * Q * sizeof(double);
-    CU(h, cudaMalloc(&h->d_scratch, n));
+int ensure_stage(lbm_handle h) {
+    if (h->d_stage[0]) return LBM_OK;
+    const size_t row_bytes = (size_t)(h->L.lnx + 2) * Q * sizeof(double);
+    size_t rows = (size_t)(64u << 20) / row_bytes;  // ~64 MB per chunk
+    rows = rows < 32 ? 32 : (rows / 32) * 32;
+    if (rows > (size_t)((h->L.ny + 2 + 31) / 32) * 32) rows = (size_t)((h->L.ny + 2 + 31) / 32) * 32;
+    h->stage_rows = (int)rows;
+    for (int b = 0; b < 2; ++b) {
+        CU(h, cudaMalloc(&h->d_stage[b], rows * row_bytes));
+        CU(h, cudaEventCreateWithFlags(&h->ev_stage_copied[b], cudaEventDisableTiming));
+        CU(h, cudaEventCreateWithFlags(&h->ev_stage_free[b], cudaEventDisableTiming));
+    }
     return LBM_OK;
 }
 
@@ -1114,6 +1127,8 @@ int create_common(const lbm_params* p, int device, int rank, int world, const vo
     if (const char* v = std::getenv("LBM_B200_TB_DEPTH")) h->tb_depth = std::min(std::max(std::atoi(v), 1), (int)TB_MAX_DEPTH);
     if (const char* v = std::getenv("LBM_B200_HALO_TIMEOUT_MS")) h->halo_timeout_ns = (unsigned long long)std::atoll(v) * 1000000ull;
     if (h->variant < 0 || h->variant > BULK_TB) h->variant = BULK_TB;
+    // default: temporal blocking where the slab is large enough to feed it (every slab of a job has the same shape)
+    if (!std::getenv("LBM_B200_VARIANT") && !tb_worthwhile(h->L)) h->variant = BULK_VEC2;
     if (world > 1) {
         h->west = rank > 0 ? rank - 1 : (h->periodic_x ? world - 1 : -1);
         h->east = rank < world - 1 ? rank + 1 : (h->periodic_x ? 0 : -1);
@@ -1248,8 +1263,12 @@ int lbm_destroy(lbm_handle h) {
         if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_slot)
         if (e) cudaEventDestroy(e);
+    for (int b = 0; b < 2; ++b) {
+        if (h->ev_stage_copied[b]) cudaEventDestroy(h->ev_stage_copied[b]);
+        if (h->ev_stage_free[b]) cudaEventDestroy(h->ev_stage_free[b]);
+    }
     cudaFree(h->f[0]); cudaFree(h->f[1]); cudaFree(h->d_mask); cudaFree(h->d_ring); cudaFree(h->d_solids);
-    cudaFree(h->d_links); cudaFree(h->d_rho); cudaFree(h->d_ux); cudaFree(h->d_uy); cudaFree(h->d_scratch);
+    cudaFree(h->d_links); cudaFree(h->d_rho); cudaFree(h->d_ux); cudaFree(h->d_uy); cudaFree(h->d_stage[0]); cudaFree(h->d_stage[1]);
     cudaFree(h->d_first_bad); cudaFree(h->d_forces); cudaFree(h->d_maxbits);
     cudaFree(h->d_red); cudaFree(h->d_gather); cudaFree(h->d_first_bad_all);
     cudaFree(h->d_flags); cudaFree(h->d_blocks_done); cudaFree(h->d_status);
@@ -1437,9 +1456,9 @@ int lbm_get_forces(lbm_handle h, double* fx, double* fy) {
     if (rc) return rc;
     { int rc_ = join_halo(h); if (rc_) return rc_; }
     if (h->aa)
-        CU(h, launch_forces(h->f[0], aa_links(h), h->n_links, h->d_forces, h->stream));
+        CU(h, launch_forces(h->f[0], aa_links(h), h->n_links, h->d_forces, h->stream, h->force_tree));
     else
-        CU(h, launch_forces(h->f[h->cur], h->d_links, h->n_links, h->d_forces, h->stream));
+        CU(h, launch_forces(h->f[h->cur], h->d_links, h->n_links, h->d_forces, h->stream, h->force_tree));
     h->launches += 1;
     double v[2];
     CU(h, cudaMemcpyAsync(v, h->d_forces, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
@@ -1482,16 +1501,28 @@ int lbm_download_f(lbm_handle h, int which, double* aos) {
     CHECK_H(h);
     if (!aos || (which != LBM_F_CURRENT && which != LBM_F_NEXT)) return fail(h, LBM_ERR_INVALID, "bad argument");
     CU(h, cudaSetDevice(h->device));
-    int rc = ensure_scratch(h);
+    int rc = ensure_stage(h);
     if (rc) return rc;
     { int rc_ = join_halo(h); if (rc_) return rc_; }
-    if (h->aa)
-        CU(h, launch_aa_export(aa_observe(h), which, h->d_scratch, h->stream));
-    else
-        CU(h, launch_export_f(observe_args(h), which, h->d_scratch, h->stream));
-    h->launches += 1;
-    const size_t n = (size_t)(h->L.lnx + 2) * (h->L.ny + 2) * Q * sizeof(double);
-    CU(h, cudaMemcpyAsync(aos, h->d_scratch, n, cudaMemcpyDeviceToHost, h->stream));
+    // chunk k: export kernel on the compute stream -> D2H on the copy stream, while the kernel of chunk k+1 runs
+    const int tny = h->L.ny + 2;
+    const size_t row_elems = (size_t)(h->L.lnx + 2) * Q;
+    int k = 0;
+    for (int row0 = 0; row0 < tny; row0 += h->stage_rows, ++k) {
+        const int b = k & 1, rows = std::min(h->stage_rows, tny - row0);
+        if (k >= 2) CU(h, cudaStreamWaitEvent(h->stream, h->ev_stage_free[b], 0));  // its last copy has left the buffer
+        if (h->aa)
+            CU(h, launch_aa_export(aa_observe(h), which, h->d_stage[b], row0, rows, h->stream));
+        else
+            CU(h, launch_export_f(observe_args(h), which, h->d_stage[b], row0, rows, h->stream));
+        h->launches += 1;
+        CU(h, cudaEventRecord(h->ev_stage_copied[b], h->stream));
+        CU(h, cudaStreamWaitEvent(h->copy_stream, h->ev_stage_copied[b], 0));
+        CU(h, cudaMemcpyAsync(aos + (size_t)row0 * row_elems, h->d_stage[b], (size_t)rows * row_elems * sizeof(double),
+                              cudaMemcpyDeviceToHost, h->copy_stream));
+        CU(h, cudaEventRecord(h->ev_stage_free[b], h->copy_stream));
+    }
+    CU(h, cudaStreamSynchronize(h->copy_stream));
     CU(h, cudaStreamSynchronize(h->stream));
     return LBM_OK;
 }
@@ -1521,7 +1552,7 @@ int lbm_upload_f(lbm_handle h, const double* aos, int iteration) {
     CHECK_H(h);
     if (!aos || iteration < 0) return fail(h, LBM_ERR_INVALID, "bad argument");
     CU(h, cudaSetDevice(h->device));
-    int rc = ensure_scratch(h);
+    int rc = ensure_stage(h);
     if (rc) return rc;
     rc = drain_forces(h);
     if (rc) return rc;
@@ -1531,10 +1562,25 @@ int lbm_upload_f(lbm_handle h, const double* aos, int iteration) {
         int rc2 = slab_barrier(h);
         if (rc2) return rc2;
     }
-    const size_t n = (size_t)(h->L.lnx + 2) * (h->L.ny + 2) * Q * sizeof(double);
-    CU(h, cudaMemcpyAsync(h->d_scratch, aos, n, cudaMemcpyHostToDevice, h->stream));
+    // chunk k: H2D on the copy stream -> transpose kernel on the compute stream, while chunk k+1 is being copied
     h->cur = 0;
-    CU(h, launch_import_f(h->d_scratch, h->f[0], h->L, h->stream));
+    {
+        const int tny = h->L.ny + 2;
+        const size_t row_elems = (size_t)(h->L.lnx + 2) * Q;
+        CU(h, cudaStreamSynchronize(h->stream));
+        int k = 0;
+        for (int row0 = 0; row0 < tny; row0 += h->stage_rows, ++k) {
+            const int b = k & 1, rows = std::min(h->stage_rows, tny - row0);
+            if (k >= 2) CU(h, cudaStreamWaitEvent(h->copy_stream, h->ev_stage_free[b], 0));  // its kernel has consumed the buffer
+            CU(h, cudaMemcpyAsync(h->d_stage[b], aos + (size_t)row0 * row_elems, (size_t)rows * row_elems * sizeof(double),
+                                  cudaMemcpyHostToDevice, h->copy_stream));
+            CU(h, cudaEventRecord(h->ev_stage_copied[b], h->copy_stream));
+            CU(h, cudaStreamWaitEvent(h->stream, h->ev_stage_copied[b], 0));
+            CU(h, launch_import_f(h->d_stage[b], h->f[0], h->L, row0, rows, h->stream));
+            CU(h, cudaEventRecord(h->ev_stage_free[b], h->stream));
+            h->launches += 1;
+        }
+    }
     const int wz = (!h->periodic_x && h->rank == 0) ? 1 : 0;
     const int ez = (!h->periodic_x && h->rank == h->world - 1) ? 1 : 0;
     if (h->aa) {
@@ -1544,7 +1590,7 @@ int lbm_upload_f(lbm_handle h, const double* aos, int iteration) {
         CU(h, launch_reset_ghosts(h->f[0], h->L, h->bc, wz, ez, h->stream));
         CU(h, launch_reset_ghosts(h->f[1], h->L, h->bc, wz, ez, h->stream));
     }
-    h->launches += 3;
+    h->launches += 2;
     const int big = INT_MAX;
     CU(h, cudaMemcpyAsync(h->d_first_bad, &big, sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
@@ -1667,6 +1713,13 @@ int lbm_get_counters(lbm_handle h, long long* launches, long long* bulk_launches
 int lbm_get_bulk_updates(lbm_handle h, long long* updates) {
     CHECK_H(h);
     if (updates) *updates = h->bulk_timed_updates;
+    return LBM_OK;
+}
+
+int lbm_set_force_mode(lbm_handle h, int mode) {
+    CHECK_H(h);
+    if (mode != LBM_FORCES_ORDERED && mode != LBM_FORCES_TREE) return fail(h, LBM_ERR_INVALID, "force mode must be 0 or 1");
+    h->force_tree = mode;
     return LBM_OK;
 }
 

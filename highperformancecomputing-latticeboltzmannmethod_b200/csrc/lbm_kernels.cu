@@ -317,6 +317,47 @@ __global__ void __launch_bounds__(256) k_forces(const double* __restrict__ f, co
     if (threadIdx.x == 32) out[1] = acc;
 }
 
+// The same sum as a fixed TREE (LBM_FORCES_TREE): every thread adds its links k = tid, tid + 1024, ... in that order,
+// then warp shuffles and one shared-memory stage combine the 1024 partial sums in a fixed pattern -- deterministic
+// from launch to launch, ~3 us whatever the link count, equal to the ordered sum to rounding (a few 1e-16 relative;
+// not bit-identical: floating-point addition is not associative).  This is the mode for dense force sampling.
+__global__ void __launch_bounds__(1024) k_forces_tree(const double* __restrict__ f, const Link* __restrict__ links,
+                                                      int n_links, double* __restrict__ out) {
+    pdl_wait();
+    pdl_release();
+    __shared__ double sx[32], sy[32];
+    double ax = 0.0, ay = 0.0;
+    for (int k = threadIdx.x; k < n_links; k += blockDim.x) {
+        const Link l = links[k];
+        const double v = f[l.off];
+        ax += (double)l.cx2 * v;
+        ay += (double)l.cy2 * v;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        ax += __shfl_down_sync(0xffffffffu, ax, s);
+        ay += __shfl_down_sync(0xffffffffu, ay, s);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        sx[threadIdx.x >> 5] = ax;
+        sy[threadIdx.x >> 5] = ay;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        ax = sx[threadIdx.x];
+        ay = sy[threadIdx.x];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            ax += __shfl_down_sync(0xffffffffu, ax, s);
+            ay += __shfl_down_sync(0xffffffffu, ay, s);
+        }
+        if (threadIdx.x == 0) {
+            out[0] = ax;
+            out[1] = ay;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Periodic extensions: copy the opposite interior edge into the ghost ring.
 __global__ void k_wrap(double* __restrict__ f, Layout L, int wrap_x, int wrap_y) {
@@ -482,11 +523,13 @@ __global__ void __launch_bounds__(256) k_maxvel(const double* __restrict__ ux, c
 // Export in the reference's padded AoS order, tile = 16 columns x 32 rows x 9 populations.
 constexpr int EX_TX = 16, EX_TY = 32;
 
-__global__ void __launch_bounds__(256) k_export_f(ObserveArgs o, int which, double* __restrict__ aos) {
+// Padded rows [row0, row0 + rows) only, `aos` pointing at the first of them: the host copy runs in chunks that
+// overlap the kernel (lbm_engine.cu).
+__global__ void __launch_bounds__(256) k_export_f(ObserveArgs o, int which, double* __restrict__ aos, int row0, int rows) {
     __shared__ double t[Q][EX_TX][EX_TY + 1];
     const Layout& L = o.L;
-    const int tnx = L.lnx + 2, tny = L.ny + 2;
-    const int gx0 = blockIdx.y * EX_TX, gy0 = blockIdx.x * EX_TY;  // padded coordinates
+    const int tnx = L.lnx + 2, tny = min(L.ny + 2, row0 + rows);
+    const int gx0 = blockIdx.y * EX_TX, gy0 = row0 + blockIdx.x * EX_TY;  // padded coordinates
     for (int c = threadIdx.x; c < EX_TX * EX_TY; c += blockDim.x) {
         const int xl = c / EX_TY, yl = c % EX_TY;
         const int gx = gx0 + xl, gy = gy0 + yl;
@@ -518,26 +561,29 @@ __global__ void __launch_bounds__(256) k_export_f(ObserveArgs o, int which, doub
         const int yl = k / (nxl * Q), e = k % (nxl * Q);
         const int gy = gy0 + yl;
         if (gy >= tny) break;
-        aos[((long long)gy * tnx + gx0) * Q + e] = t[e % Q][e / Q][yl];
+        aos[((long long)(gy - row0) * tnx + gx0) * Q + e] = t[e % Q][e / Q][yl];
     }
 }
 
-__global__ void __launch_bounds__(256) k_import_f(const double* __restrict__ aos, double* __restrict__ f, Layout L) {
+// The interior cells of padded rows [row0, row0 + rows), `aos` pointing at the first of those rows.
+__global__ void __launch_bounds__(256) k_import_f(const double* __restrict__ aos, double* __restrict__ f, Layout L, int row0,
+                                                  int rows) {
     __shared__ double t[Q][EX_TX][EX_TY + 1];
     const int tnx = L.lnx + 2;
-    const int x0 = blockIdx.y * EX_TX, y0 = blockIdx.x * EX_TY;  // interior coordinates
+    const int x0 = blockIdx.y * EX_TX, gy0 = row0 + blockIdx.x * EX_TY;
+    const int gy_end = min(L.ny + 1, row0 + rows);  // one past the last interior padded row of the chunk
     const int nxl = min(EX_TX, L.lnx - x0);
     for (int k = threadIdx.x; k < EX_TY * nxl * Q; k += blockDim.x) {
         const int yl = k / (nxl * Q), e = k % (nxl * Q);
-        const int y = y0 + yl;
-        if (y >= L.ny) break;
-        t[e % Q][e / Q][yl] = aos[((long long)(y + 1) * tnx + (x0 + 1)) * Q + e];
+        const int gy = gy0 + yl;
+        if (gy >= gy_end) break;
+        if (gy >= 1) t[e % Q][e / Q][yl] = aos[((long long)(gy - row0) * tnx + (x0 + 1)) * Q + e];
     }
     __syncthreads();
     for (int k = threadIdx.x; k < Q * EX_TX * EX_TY; k += blockDim.x) {
         const int i = k / (EX_TX * EX_TY), xl = (k / EX_TY) % EX_TX, yl = k % EX_TY;
-        const int x = x0 + xl, y = y0 + yl;
-        if (x < L.lnx && y < L.ny) f[i * L.plane + L.at(x + 1, y)] = t[i][xl][yl];
+        const int x = x0 + xl, gy = gy0 + yl;
+        if (x < L.lnx && gy >= 1 && gy < gy_end) f[i * L.plane + L.at(x + 1, gy - 1)] = t[i][xl][yl];
     }
 }
 
@@ -612,7 +658,8 @@ cudaError_t launch_wait_halo(const P2pArgs& x, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_forces(const double* f_next, const Link* links, int n_links, double* out, cudaStream_t s) {
+cudaError_t launch_forces(const double* f_next, const Link* links, int n_links, double* out, cudaStream_t s, int tree) {
+    if (tree) return launch_chain(k_forces_tree, dim3(1), dim3(1024), s, f_next, links, n_links, out);
     return launch_chain(k_forces, dim3(1), dim3(256), s, f_next, links, n_links, out);
 }
 
@@ -659,15 +706,15 @@ cudaError_t launch_maxvel(const double* ux, const double* uy, long long n, unsig
     return cudaGetLastError();
 }
 
-cudaError_t launch_export_f(const ObserveArgs& o, int which, double* aos, cudaStream_t s) {
-    dim3 grid(cdiv(o.L.ny + 2, EX_TY), cdiv(o.L.lnx + 2, EX_TX));
-    k_export_f<<<grid, 256, 0, s>>>(o, which, aos);
+cudaError_t launch_export_f(const ObserveArgs& o, int which, double* aos, int row0, int rows, cudaStream_t s) {
+    dim3 grid(cdiv(rows, EX_TY), cdiv(o.L.lnx + 2, EX_TX));
+    k_export_f<<<grid, 256, 0, s>>>(o, which, aos, row0, rows);
     return cudaGetLastError();
 }
 
-cudaError_t launch_import_f(const double* aos, double* f, const Layout& L, cudaStream_t s) {
-    dim3 grid(cdiv(L.ny, EX_TY), cdiv(L.lnx, EX_TX));
-    k_import_f<<<grid, 256, 0, s>>>(aos, f, L);
+cudaError_t launch_import_f(const double* aos, double* f, const Layout& L, int row0, int rows, cudaStream_t s) {
+    dim3 grid(cdiv(rows, EX_TY), cdiv(L.lnx, EX_TX));
+    k_import_f<<<grid, 256, 0, s>>>(aos, f, L, row0, rows);
     return cudaGetLastError();
 }
 

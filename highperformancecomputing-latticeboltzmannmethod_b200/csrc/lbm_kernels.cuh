@@ -80,7 +80,10 @@ cudaError_t launch_fixup_p2p(bool pull, const StepArgs& a, const BcArgs& b, cons
 cudaError_t launch_wait_halo(const P2pArgs& x, cudaStream_t s);
 
 // Momentum-exchange reduction (reference include/LBMIO.h:114-162) over a precomputed link list.
-cudaError_t launch_forces(const double* f_next, const Link* links, int n_links, double* out_fx_fy, cudaStream_t s);
+// tree = 0: terms added one by one in the reference's (y, x, i) order (its bits, forces.csv byte for byte);
+// tree = 1: fixed parallel reduction tree (deterministic, a few us, equal to rounding).
+cudaError_t launch_forces(const double* f_next, const Link* links, int n_links, double* out_fx_fy, cudaStream_t s,
+                          int tree = 0);
 
 // Ghost wrap for the periodic extensions.
 cudaError_t launch_wrap(double* f, const Layout& L, int wrap_x, int wrap_y, cudaStream_t s);
@@ -109,8 +112,9 @@ cudaError_t launch_macros(const ObserveArgs& o, double* rho, double* ux, double*
 cudaError_t launch_maxvel(const double* ux, const double* uy, long long n, unsigned long long* out_bits,
                           cudaStream_t s);
 // f_current / f_next in the reference's padded AoS order.
-cudaError_t launch_export_f(const ObserveArgs& o, int which, double* aos, cudaStream_t s);
-cudaError_t launch_import_f(const double* aos, double* f, const Layout& L, cudaStream_t s);
+// ... of the padded rows [row0, row0 + rows), `aos` pointing at the first of them (row0 a multiple of 32)
+cudaError_t launch_export_f(const ObserveArgs& o, int which, double* aos, int row0, int rows, cudaStream_t s);
+cudaError_t launch_import_f(const double* aos, double* f, const Layout& L, int row0, int rows, cudaStream_t s);
 // Ghost ring of one buffer back to the convention (W/E domain-edge columns 0, everything else e).
 cudaError_t launch_reset_ghosts(double* f, const Layout& L, const BcArgs& b, int west_zero, int east_zero,
                                 cudaStream_t s);
@@ -159,7 +163,7 @@ cudaError_t launch_aa_fix_odd(const AaArgs& a, const BcArgs& b, const int2* ring
 cudaError_t launch_aa_unwrap(double* f, const Layout& L, int do_x, int do_y, cudaStream_t s);
 cudaError_t launch_aa_ghosts(double* f, const Layout& L, const BcArgs& b, int west_zero, int east_zero, cudaStream_t s);
 cudaError_t launch_aa_macros(const AaObserve& o, double* rho, double* ux, double* uy, cudaStream_t s);
-cudaError_t launch_aa_export(const AaObserve& o, int which, double* aos, cudaStream_t s);
+cudaError_t launch_aa_export(const AaObserve& o, int which, double* aos, int row0, int rows, cudaStream_t s);
 cudaError_t launch_aa_check(const AaObserve& o, int* first_bad, int bad_iter, cudaStream_t s);
 
 // The solid run of column x, or an empty one (no load at all outside [col_lo, col_hi)).

@@ -14,8 +14,10 @@ namespace {
 // job the blocks of chunks 0 and 1 (the slab-edge columns) run the peer-memory hand-shake around their
 // march: they are the first blocks of the grid, so the neighbours get their halo while the interior
 // chunks are still being worked on.
+// Occupancy: the ring of a depth-2 pass (72 B per thread and slot) lets 768 threads share an SM's shared memory; the
+// launch bound asks for exactly that, i.e. at most 85 registers per thread.
 template <int T, int B, bool FORCED>
-__global__ void __launch_bounds__(B) k_tb(TbArgs a, int p2p) {
+__global__ void __launch_bounds__(B, (T == 3 ? 256 : 768) / B) k_tb(const __grid_constant__ TbArgs a, int p2p) {
     extern __shared__ double ring[];
     pdl_wait();
     pdl_release();
@@ -105,17 +107,11 @@ cudaError_t launch_one(TbArgs a, bool p2p, cudaStream_t s) {
     if (ncols > 0) {
         int xc = env_int("LBM_B200_TB_XC", 0);
         if (xc <= 0) {
-            // columns per chunk: about 128 (1.6 % redundant columns at depth 2), adjusted so that the grid is a
-            // whole number of waves of resident blocks -- a marching block lives as long as 1/waves of the kernel
-            const int target = 128;
-            const long long blocks0 = (long long)strips * cdiv(ncols, target) + (p2p ? 2 * strips : 0);
-            long long waves = (blocks0 + slots / 2) / slots;
-            if (waves < 1) waves = 1;
-            long long c = (waves * slots - (p2p ? 2 * strips : 0)) / strips;
-            if (c < 1) c = 1;
-            if (c > ncols) c = ncols;
-            xc = cdiv(ncols, c);
-            if (xc < 16 && ncols >= 16) xc = 16;
+            // 64 columns per chunk (3 % redundant columns at depth 2; measured best on a 4096 x 8192 slab: shorter
+            // chunks keep the strips of a column in step and the tail of the grid short), fewer where that
+            // leaves the device with less than two waves of resident blocks
+            xc = 64;
+            while (xc > 16 && (long long)strips * cdiv(ncols, xc) < 2LL * slots) xc /= 2;
         }
         a.xc = xc;
         chunks = cdiv(ncols, xc);
@@ -145,8 +141,8 @@ cudaError_t launch_forced(const TbArgs& a, bool p2p, cudaStream_t s) {
 
 int block_threads() {
     static const int b = [] {
-        const int v = env_int("LBM_B200_TB_B", 256);
-        return v == 128 ? 128 : 256;
+        const int v = env_int("LBM_B200_TB_B", 128);
+        return v == 256 ? 256 : 128;
     }();
     return b;
 }
@@ -155,12 +151,23 @@ int block_threads() {
 
 cudaError_t launch_tb(int depth, TbArgs a, bool p2p, cudaStream_t s) {
     const bool small = block_threads() == 128;
+    tb_fill_offsets(a);
+    a.pf_dist = env_int("LBM_B200_TB_PF", 1);
     switch (depth) {
         case 1: return small ? launch_forced<1, 128>(a, p2p, s) : launch_forced<1, 256>(a, p2p, s);
         case 2: return small ? launch_forced<2, 128>(a, p2p, s) : launch_forced<2, 256>(a, p2p, s);
         case 3: return launch_forced<3, 256>(a, p2p, s);
         default: return cudaErrorInvalidValue;
     }
+}
+
+// Whether a slab of this shape gives the marching blocks enough parallelism to beat the one-iteration kernels:
+// at least two waves of resident blocks with 64-column chunks.  Small lattices (the reference's default 2048 x 512
+// lives in L2 anyway) stay on the bulk kernels.
+bool tb_worthwhile(const Layout& L) {
+    const int b = block_threads();
+    const long long blocks = (long long)cdiv(L.ny, b - 4) * cdiv(L.lnx, 64);
+    return blocks >= 2LL * 148 * (768 / b);
 }
 
 int tb_rows_per_block(int depth) {

@@ -61,19 +61,49 @@ struct TbArgs {
     // the slab's native order [x*ny + y]; nullptr: not wanted
     double *m_rho, *m_ux, *m_uy;
     P2pArgs px;  // multi-slab: peer buffers and the hand-shake words (lbm_kernels.cuh)
+    // BYTE offsets relative to (plane 0, column c, row y), filled in by tb_fill_offsets: population i is PULLED
+    // from ld_off[i] = 8 (i*plane - c_ix*PY - c_iy) and stored at st_off[i] = 8 i*plane; col_bytes = 8 PY.  Kernel
+    // parameters, so that an address is one 64-bit add of a constant-bank operand to a per-thread pointer.
+    long long ld_off[Q], st_off[Q], col_bytes;
+    long long pf_off[Q];  // 8 (i*plane - c_ix*PY): the column segment population i is pulled from, 16-byte aligned
+    int pf_dist;          // columns the L2 prefetch runs ahead of the loads (0: off)
 };
+
+inline void tb_fill_offsets(TbArgs& a) {
+    for (int i = 0; i < Q; ++i) {
+        a.ld_off[i] = 8 * ((long long)i * a.L.plane - (long long)cxi(i) * a.L.PY - cyi(i));
+        a.st_off[i] = 8 * (long long)i * a.L.plane;
+        a.pf_off[i] = 8 * ((long long)i * a.L.plane - (long long)cxi(i) * a.L.PY);
+    }
+    a.col_bytes = 8 * (long long)a.L.PY;
+}
+
+// Keeps a per-thread pointer in its registers as ONE 64-bit value (the compiler would otherwise re-derive it from
+// base + 8*index at every use: four integer instructions per access instead of two).
+template <class P>
+LBM_HD P tb_opaque(P p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("" : "+l"(p));
+#endif
+    return p;
+}
 
 // ---- host / device glue (the host side exists for the thread-for-thread emulation only) ----------
 #if defined(__CUDA_ARCH__)
 #define TB_SYNC() __syncthreads()
 #define TB_LD(p, coherent) ((coherent) ? __ldcg(p) : __ldg(p))
 #define TB_FLAG(ptr, v) atomicMin((ptr), (v))
+// (the per-thread pointers are opaque 64-bit values, see tb_opaque: say "global" explicitly)
+#define TB_ST(ptr, v) asm volatile("st.global.f64 [%0], %1;" ::"l"(ptr), "d"(v) : "memory")
+#define TB_COLD __device__ __host__ __noinline__
 #else
 void tb_host_sync();
 void tb_host_flag(int* p, int v);
 #define TB_SYNC() tb_host_sync()
 #define TB_LD(p, coherent) (*(p))
 #define TB_FLAG(ptr, v) tb_host_flag((ptr), (v))
+#define TB_ST(ptr, v) (*reinterpret_cast<double*>(ptr) = (v))
+#define TB_COLD inline
 #endif
 
 LBM_HD int tb_wrap(int v, int n) {
@@ -103,212 +133,397 @@ LBM_HD void tb_chunk(const TbArgs& a, int chunk, int& x0, int& x1, bool& edge) {
     x1 = x0 + a.xc < a.x_end ? x0 + a.xc : a.x_end;
 }
 
+// What one thread holds for one cell of one stage.
+struct TbCell {
+    double f[Q];
+    int kind;  // 0: nothing here; 1: pulled populations, still to be ruled / checked / collided;
+               // 2: ghost row (eq(1,u_in,0)); 3: ghost column at a physical edge (0.0); 4: obstacle cell whose
+               // eight neighbours are solid (w, nothing to check)
+    int m;     // mask byte of the cell (kind 1): 0 fluid, 1 solid
+    int xr;    // its slab column (wrapped in a periodic slab)
+};
+
+// The thread's fixed view of its row and of the block's chunk.
+template <int T, int B>
+struct TbRow {
+    int tid, y, yr, row_kind;  // row kinds: 0 dead, 1 a cell to compute (row yr), 2 ghost row holding eq(1,u_in,0)
+    bool wall_b, wall_t, out_row, edge;
+    bool strip_walls;          // (uniform over the block) some row of this strip is a wall row
+    int x0, x1;
+    const char* srow;  // a.src + the offset of row yr inside a column (column gx = -XO)
+    char* drow;        // a.dst + the offset of row y
+    bool on[T];          // stage k works on this row
+    const char* pf_seg;  // (uniform) start of the block's row segment in column gx = -XO of plane 0, 16-byte aligned
+    int pf_bytes;        // (uniform) its length; 0: no L2 prefetch
+    int pf_last;         // (uniform) last column worth prefetching: the end of this block's own march
+};
+
+// Column kind for stage k (uniform over the block): 0 dead, 1 compute cell column xr, 2 ghost column at a physical
+// edge (0.0; corners: e).
+template <int T>
+LBM_HD int tb_col_kind(const TbArgs& a, int x0, int x1, int k, int c, int& xr) {
+    const int grow = T - k;  // how far stage k reaches beyond the columns the block stores
+    const int lnx = a.L.lnx;
+    xr = c;
+    if (c < x0 - grow || c >= x1 + grow) return 0;
+    if (c >= 0 && c < lnx) return 1;
+    const int mode = c < 0 ? a.west : a.east;
+    if (mode == TB_EDGE_WRAP) { xr = tb_wrap(c, lnx); return 1; }
+    if (mode == TB_EDGE_HALO) return 1;  // (inside the halo by construction of the chunks)
+    return (c == -1 || c == lnx) ? 2 : 0;
+}
+
+// Classification shared by both halves of a stage.  PLAIN: the caller guarantees an interior column that is
+// neither the inlet nor the outlet column and lies inside the stage's range (no column logic at all);
+// MASKED = false: ... and no obstacle cell in it (no mask load either).
+template <int T, int B, bool PLAIN>
+LBM_HD void tb_classify(const TbArgs& a, const TbRow<T, B>& r, int k, int c, bool masked, TbCell& cell) {
+    cell.kind = 0;
+    cell.m = 0;
+    cell.xr = c;
+    if (!r.on[k - 1]) return;
+    int col_kind = 1;
+    if (!PLAIN) {
+        col_kind = tb_col_kind<T>(a, r.x0, r.x1, k, c, cell.xr);
+        if (col_kind == 0) return;
+    }
+    if (r.row_kind == 2) { cell.kind = 2; return; }
+    if (!PLAIN && col_kind == 2) { cell.kind = 3; return; }
+    cell.kind = 1;
+    if (masked) {
+        const int gx = cell.xr + 1;
+        if (gx >= a.mask_lo && gx < a.mask_hi) {
+            cell.m = a.mask[a.L.at(gx, r.yr)];
+            if (cell.m == 2) cell.kind = 4;
+        }
+    }
+}
+
+// Stage 1, first half: classify the cell (c, row) and ISSUE its nine loads.  Called one march step ahead of
+// tb_finish, so that the loads of column s+1 are in flight while columns s, s-1, ... are being computed.
+// Periodic edges are addressed naturally: the ghost rows / columns hold wrapped copies (k_wrap after every pass).
+template <int T, int B, bool PLAIN>
+LBM_HD void tb_issue(const TbArgs& a, const TbRow<T, B>& r, int c, bool masked, TbCell& cell) {
+    tb_classify<T, B, PLAIN>(a, r, 1, c, masked, cell);
+    if (cell.kind != 1) return;
+    const char* p = r.srow + (long long)(cell.xr + 1 + Layout::XO) * a.col_bytes;
+    // the lean path never runs in a slab-edge chunk: one flavour of load
+    const bool coherent = PLAIN ? false : r.edge;
+    if ((T > 1) || a.pull) {
+        // population i comes from column xr - c_ix, row yr - c_iy (reference include/LBMSolver.h:138-142)
+#pragma unroll
+        for (int i = 0; i < Q; ++i) cell.f[i] = TB_LD(reinterpret_cast<const double*>(p + a.ld_off[i]), coherent);
+    } else {
+#pragma unroll
+        for (int i = 0; i < Q; ++i) cell.f[i] = TB_LD(reinterpret_cast<const double*>(p + a.st_off[i]), coherent);
+    }
+}
+
+// Stage k >= 2, first half: the same cell from stage k-1's ring in shared memory.
+template <int T, int B, bool PLAIN>
+LBM_HD void tb_from_ring(const TbArgs& a, const TbRow<T, B>& r, const double* ring, int k, int c, bool masked, TbCell& cell) {
+    tb_classify<T, B, PLAIN>(a, r, k, c, masked, cell);
+    if (cell.kind != 1) return;
+    const double* g = ring + (k - 2) * (TB_SLOTS * Q * B) + r.tid;
+    const double* gw = g + ((c - 1) & (TB_SLOTS - 1)) * (Q * B);
+    const double* g0 = g + (c & (TB_SLOTS - 1)) * (Q * B);
+    const double* ge = g + ((c + 1) & (TB_SLOTS - 1)) * (Q * B);
+    cell.f[0] = g0[0 * B];
+    cell.f[1] = gw[1 * B];
+    cell.f[2] = g0[2 * B - 1];
+    cell.f[3] = ge[3 * B];
+    cell.f[4] = g0[4 * B + 1];
+    cell.f[5] = gw[5 * B - 1];
+    cell.f[6] = ge[6 * B - 1];
+    cell.f[7] = ge[7 * B + 1];
+    cell.f[8] = gw[8 * B + 1];
+}
+
+// (cold, kept out of line: the hot loop should fit the instruction cache) a constant cell into stage k's ring
+// which: 2 eq(1,u_in,0), 3 zero, 4 w (the kinds of TbCell).  `a` is a __grid_constant__ kernel parameter: taking its
+// address costs nothing.
+template <int B>
+TB_COLD void tb_ring_const(double* w, const TbArgs& a, int which) {
+    if (which == 3) {
+#pragma unroll
+        for (int i = 0; i < Q; ++i) w[i * B] = 0.0;
+        return;
+    }
+    const double* v = which == 2 ? a.bc.e : a.bc.w;
+#pragma unroll
+    for (int i = 0; i < Q; ++i) w[i * B] = v[i];
+}
+
+// The last stage's populations of an edge column into the neighbours' ghost columns (peer memory over NVLink).
+// Column lnx-1-d goes to the east neighbour's ghost column gx = -d.  What it needs of that column, for a pass of
+// depth halo_w: the populations moving towards it (1,5,8) always; the ones that stay in the column (0,2,4) where
+// it recomputes the column itself (d <= halo_w-2); the ones moving away (3,6,7) where it also recomputes the
+// column beyond (d <= halo_w-3).
+template <int T, int B>
+LBM_HD void tb_push(const TbArgs& a, const TbRow<T, B>& r, int c, const double* f) {
+    const Layout& L = a.L;
+    const int lnx = L.lnx;
+    const int de = lnx - 1 - c, dw = c;
+    if (a.px.peer_dst_east && de < a.halo_w) {
+        double* q = a.px.peer_dst_east + L.at(-de, r.y);
+        q[1 * L.plane] = f[1];
+        q[5 * L.plane] = f[5];
+        q[8 * L.plane] = f[8];
+        if (de <= a.halo_w - 2) {
+            q[0 * L.plane] = f[0];
+            q[2 * L.plane] = f[2];
+            q[4 * L.plane] = f[4];
+        }
+        if (de <= a.halo_w - 3) {
+            q[3 * L.plane] = f[3];
+            q[6 * L.plane] = f[6];
+            q[7 * L.plane] = f[7];
+        }
+    }
+    if (a.px.peer_dst_west && dw < a.halo_w) {
+        double* q = a.px.peer_dst_west + L.at(lnx + 1 + dw, r.y);
+        q[3 * L.plane] = f[3];
+        q[6 * L.plane] = f[6];
+        q[7 * L.plane] = f[7];
+        if (dw <= a.halo_w - 2) {
+            q[0 * L.plane] = f[0];
+            q[2 * L.plane] = f[2];
+            q[4 * L.plane] = f[4];
+        }
+        if (dw <= a.halo_w - 3) {
+            q[1 * L.plane] = f[1];
+            q[5 * L.plane] = f[5];
+            q[8 * L.plane] = f[8];
+        }
+    }
+}
+
+// Second half of every stage: boundary rules, stability check, collision; then the ring (k < T) or HBM and the
+// neighbours' ghost columns (k == T).  Returns true when a checked value was unstable.
+template <int T, int B, bool FORCED, bool PLAIN>
+LBM_HD bool tb_finish(const TbArgs& a, const TbRow<T, B>& r, double* ring, int k, int c, TbCell& cell) {
+    const Layout& L = a.L;
+    const int lnx = L.lnx, ny = L.ny;
+    if (cell.kind == 0) return false;
+    double* w = ring + (k - 1) * (TB_SLOTS * Q * B) + (c & (TB_SLOTS - 1)) * (Q * B) + r.tid;  // (k < T only)
+    if (cell.kind != 1) {
+        // ---- cold: constants.  Written from the argument block straight to the ring: nothing is merged into the
+        // registers of the hot path.
+        if (k < T) {
+            tb_ring_const<B>(w, a, cell.kind);
+        } else if (cell.kind == 4) {
+            if (a.m_rho) {  // include/LBMSolver.h:260-261; rho keeps the constructor's 1.0
+                const long long g = (long long)c * ny + r.y;
+                a.m_rho[g] = 1.0;
+                a.m_ux[g] = 0.0;
+                a.m_uy[g] = 0.0;
+            }
+            if (T == 1 && !a.pull && a.write) {
+                char* q = r.drow + (long long)(c + 1 + Layout::XO) * a.col_bytes;
+#pragma unroll
+                for (int i = 0; i < Q; ++i) TB_ST(q + a.st_off[i], a.bc.w[i]);
+            }
+            if (!PLAIN && r.edge && a.write) tb_push<T, B>(a, r, c, a.bc.w);  // the neighbour pulls w from here
+        }
+        return false;
+    }
+    bool bad = false;
+    double* f = cell.f;
+    const bool rules = (T > 1) || a.pull;  // the first iteration has no boundary pass before it
+    if (rules && cell.m == 0) {
+        // the reference's serial order: bottom, top, inlet, outlet
+        if (r.strip_walls) {
+            if (r.wall_b) wall_bottom(f);
+            if (r.wall_t) wall_top(f);
+        }
+        if (!PLAIN) {
+            if (a.bc.inlet && cell.xr == 0) (void)zou_he_inlet(f, a.bc.u_in);
+            if (a.bc.outlet && cell.xr == lnx - 1) (void)zou_he_outlet(f);
+        }
+    }
+    if (rules) {
+#pragma unroll
+        for (int i = 0; i < Q; ++i) bad |= unstable_value(f[i]);
+    }
+    if (cell.m != 0) {
+        // ---- cold: an obstacle cell with a fluid neighbour: checked (the reference's check sees what streams into
+        // it), then w for ever
+        if (k < T) {
+            tb_ring_const<B>(w, a, 4);
+        } else {
+            if (a.m_rho) {
+                const long long g = (long long)c * ny + r.y;
+                a.m_rho[g] = 1.0;
+                a.m_ux[g] = 0.0;
+                a.m_uy[g] = 0.0;
+            }
+            if (a.write) {
+                // never stored -- except by the first iteration after an upload, whose destination may hold anything
+                char* q = r.drow + (long long)(c + 1 + Layout::XO) * a.col_bytes;
+                if (T == 1 && !a.pull) {
+#pragma unroll
+                    for (int i = 0; i < Q; ++i) TB_ST(q + a.st_off[i], a.bc.w[i]);
+                }
+                if (!PLAIN && r.edge) tb_push<T, B>(a, r, c, a.bc.w);
+            }
+        }
+        return bad;
+    } else {
+        const Moments mo = moments(f);
+        if (k == T && a.m_rho) {
+            const long long g = (long long)c * ny + r.y;
+            a.m_rho[g] = mo.rho;
+            a.m_ux[g] = mo.ux;
+            a.m_uy[g] = mo.uy;
+        }
+        if (FORCED)
+            bgk_forced(f, mo, a.tau_inv, a.Fx, a.Fy, f);
+        else
+            bgk(f, mo, a.tau_inv, f);
+        if (k < T) {
+#pragma unroll
+            for (int i = 0; i < Q; ++i) w[i * B] = f[i];
+            return bad;
+        }
+        if (!a.write) return bad;
+        // ---- the last stage: HBM ...
+        char* q = r.drow + (long long)(c + 1 + Layout::XO) * a.col_bytes;
+#pragma unroll
+        for (int i = 0; i < Q; ++i) TB_ST(q + a.st_off[i], f[i]);
+    }
+    if (!PLAIN && r.edge) tb_push<T, B>(a, r, c, f);  // ... and the neighbours' ghost columns over NVLink
+    return bad;
+}
+
+// L2 prefetch, by the bulk-copy engine: ONE thread of the block asks for the nine column segments the block's loads
+// of march step `col` will touch (cp.async.bulk.prefetch.L2: a 2 KB segment per instruction, no register, no
+// scoreboard).  The register prefetch of tb_step covers one step; a step is shorter than a trip to HBM, so the lines
+// are pulled into L2 pf_dist steps earlier.
+template <int T, int B>
+LBM_HD void tb_prefetch_l2(const TbArgs& a, const char* seg, int bytes, int col) {
+#if defined(__CUDA_ARCH__)
+    if (col > a.L.lnx) return;
+    const char* p = seg + (long long)(col + 1 + Layout::XO) * a.col_bytes;
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p + a.pf_off[i]), "r"(bytes) : "memory");
+#else
+    (void)a; (void)seg; (void)bytes; (void)col;
+#endif
+}
+
+// One march step: stage 1 on column s (`cur`: its loads were issued a step ago), stages 2..T behind it, and the
+// loads of column s+1 into `nxt`.  PLAIN: see tb_classify; masked (uniform): the columns this step touches may hold
+// obstacle cells.
+template <int T, int B, bool FORCED, bool PLAIN>
+LBM_HD void tb_step(const TbArgs& a, const TbRow<T, B>& r, double* ring, int s, bool issue_next, bool masked, TbCell& cur,
+                    TbCell& nxt, bool bad[T]) {
+    if (r.tid == 0 && r.pf_bytes > 0 && s + 1 + a.pf_dist <= r.pf_last) tb_prefetch_l2<T, B>(a, r.pf_seg, r.pf_bytes, s + 1 + a.pf_dist);
+    if (issue_next) tb_issue<T, B, PLAIN>(a, r, s + 1, masked, nxt);
+    bad[0] |= tb_finish<T, B, FORCED, PLAIN>(a, r, ring, 1, s, cur);
+#pragma unroll
+    for (int k = 2; k <= T; ++k) {
+        TB_SYNC();  // stage k-1's column of this step is in its ring
+        tb_from_ring<T, B, PLAIN>(a, r, ring, k, s - (k - 1), masked, cur);
+        bad[k - 1] |= tb_finish<T, B, FORCED, PLAIN>(a, r, ring, k, s - (k - 1), cur);
+    }
+}
+
 // One thread of one block: `tid` in [0, B), rows of strip `strip`, columns of chunk `chunk`.
 // `ring` is the block's shared memory (TbShape::RING_DOUBLES doubles).
 template <int T, int B, bool FORCED>
 LBM_HD void tb_thread(const TbArgs& a, double* ring, int tid, int strip, int chunk) {
     using S = TbShape<T, B>;
-    const Layout& L = a.L;
-    const int lnx = L.lnx, ny = L.ny;
-    int x0, x1;
-    bool edge;
-    tb_chunk(a, chunk, x0, x1, edge);
-    if (x0 >= x1) return;  // (uniform over the block)
+    const int ny = a.L.ny, lnx = a.L.lnx;
+    TbRow<T, B> r;
+    tb_chunk(a, chunk, r.x0, r.x1, r.edge);
+    if (r.x0 >= r.x1) return;  // (uniform over the block)
 
     // ---- this thread's row -------------------------------------------------------------------
-    const int ys = strip * S::H;
-    const int y = ys - S::ROFF + tid;
-    // row kinds: 0 dead, 1 a cell to compute (row yr), 2 ghost row holding eq(1,u_in,0)
-    int row_kind, yr = y;
+    r.tid = tid;
+    r.y = strip * S::H - S::ROFF + tid;
+    r.yr = r.y;
     if (a.periodic_y) {
-        row_kind = (y >= -(T - 1) && y < ny + (T - 1)) ? 1 : 0;
-        yr = tb_wrap(y, ny);
+        r.row_kind = (r.y >= -(T - 1) && r.y < ny + (T - 1)) ? 1 : 0;
+        r.yr = tb_wrap(r.y, ny);
     } else {
-        row_kind = (y >= 0 && y < ny) ? 1 : ((y == -1 || y == ny) ? 2 : 0);
+        r.row_kind = (r.y >= 0 && r.y < ny) ? 1 : ((r.y == -1 || r.y == ny) ? 2 : 0);
     }
-    // rows the pulls of row yr read: yr-1, yr, yr+1 (ghost rows -1 and ny exist in memory)
-    int o_m = Layout::YO + yr - 1, o_0 = Layout::YO + yr, o_p = Layout::YO + yr + 1;
-    if (a.periodic_y) {
-        o_m = Layout::YO + tb_wrap(yr - 1, ny);
-        o_p = Layout::YO + tb_wrap(yr + 1, ny);
+    r.wall_b = a.bc.walls && r.yr == 0;
+    r.wall_t = a.bc.walls && r.yr == ny - 1;
+    {
+        const int lo = strip * S::H - S::ROFF, hi = lo + B;  // rows of this block
+        r.strip_walls = a.bc.walls && ((lo <= 0 && hi > 0) || (lo <= ny - 1 && hi > ny - 1) || a.periodic_y);
     }
-    const bool wall_b = a.bc.walls && yr == 0, wall_t = a.bc.walls && yr == ny - 1;
-    const bool out_row = (tid >= S::ROFF && tid < S::ROFF + S::H && y >= 0 && y < ny);  // rows the last stage stores
+    r.out_row = (tid >= S::ROFF && tid < S::ROFF + S::H && r.y >= 0 && r.y < ny);  // rows the last stage stores
+#pragma unroll
+    for (int k = 1; k <= T; ++k) {
+        const int grow = T - k;  // how far stage k reaches beyond the rows the block stores
+        r.on[k - 1] = r.row_kind != 0 && tid >= S::ROFF - grow && tid < S::ROFF + S::H + grow && (k < T || r.out_row);
+    }
+    r.srow = tb_opaque(reinterpret_cast<const char*>(a.src + (Layout::YO + r.yr)));
+    r.drow = tb_opaque(reinterpret_cast<char*>(a.dst + (Layout::YO + r.y)));
+    r.pf_bytes = 0;
+    r.pf_seg = nullptr;
+    if (a.pf_dist > 0) {
+        // the rows the block's pulls touch, [strip*H - ROFF - 1, ... + B + 2), widened to whole 16-byte pairs and
+        // clipped to the column
+        int first = strip * S::H - S::ROFF - 1;
+        int last = first + B + 2;
+        if (first < -Layout::YO) first = -Layout::YO;
+        if (last > a.L.PY - Layout::YO) last = a.L.PY - Layout::YO;
+        first &= ~1;
+        last = (last + 1) & ~1;
+        if (last > first) {
+            r.pf_seg = reinterpret_cast<const char*>(a.src + (Layout::YO + first));
+            r.pf_bytes = (last - first) * 8;
+        }
+    }
     bool bad[T];
 #pragma unroll
     for (int k = 0; k < T; ++k) bad[k] = false;
 
-    const int s_first = x0 - (T - 1), s_last = x1 + (T - 2);
-    for (int s = s_first; s <= s_last; ++s) {
-#pragma unroll
-        for (int k = 1; k <= T; ++k) {
-            const int c = s - (k - 1);  // the column stage k works on
-            const int grow = T - k;     // how far stage k reaches beyond the rows / columns the block stores
-            // ---- column kind (uniform over the block) --------------------------------------------
-            // 0 dead, 1 compute cell column xr, 2 ghost column at a physical edge (0.0; corners: e)
-            int col_kind = 0, xr = c;
-            if (c >= x0 - grow && c < x1 + grow) {
-                if (c >= 0 && c < lnx) col_kind = 1;
-                else {
-                    const int mode = c < 0 ? a.west : a.east;
-                    if (mode == TB_EDGE_WRAP) { col_kind = 1; xr = tb_wrap(c, lnx); }
-                    else if (mode == TB_EDGE_HALO) col_kind = 1;  // (inside the halo by construction of the chunks)
-                    else col_kind = (c == -1 || c == lnx) ? 2 : 0;
-                }
+    // ---- the march ---------------------------------------------------------------------------------
+    // Steps whose T columns s, s-1, ..., s-(T-1) are all plain interior columns (not a ghost column, not the inlet
+    // or outlet column) with every stage inside its range take the lean path; [p0, p1) also keeps column s+1 plain.
+    const int s_first = r.x0 - (T - 1), s_last = r.x1 + (T - 2);
+    const int c_lo = (a.west == TB_EDGE_CONST && a.bc.inlet) ? 1 : 0;           // first plain column
+    const int c_hi = (a.east == TB_EDGE_CONST && a.bc.outlet) ? lnx - 1 : lnx;  // one past the last plain column
+    int p0 = r.x0 + (T - 1), p1 = s_last;  // every stage active for s in [x0+T-1, s_last]; s+1 <= s_last
+    if (p0 < c_lo + (T - 1)) p0 = c_lo + (T - 1);
+    if (p1 > c_hi - 1) p1 = c_hi - 1;
+    if (r.edge) p1 = p0;  // the few slab-edge columns also feed the neighbour: general path
+    r.pf_last = s_last < lnx ? s_last : lnx;
+    // Two cells take turns: while one is being computed the other one's loads (the next column) are in flight.
+    TbCell ca, cb;
+    tb_issue<T, B, false>(a, r, s_first, true, ca);
+    int s = s_first;
+    bool a_is_cur = true;
+    // the columns s-(T-1) .. s+1 a step touches may hold obstacle cells iff they meet [mask_lo - 1, mask_hi - 1)
+    const int m0 = a.mask_lo - 2, m1 = a.mask_hi - 1 + (T - 1);  // steps s in [m0, m1) are masked
+    while (s <= s_last) {
+        if (s >= p0 && s < p1) {
+            // a stretch of lean steps, unrolled by two so that the two cells keep their roles (no register copies)
+            if (!a_is_cur) {
+                tb_step<T, B, FORCED, true>(a, r, ring, s, true, s >= m0 && s < m1, cb, ca, bad);
+                a_is_cur = true;
+                ++s;
             }
-            const bool row_on = row_kind != 0 && tid >= S::ROFF - grow && tid < S::ROFF + S::H + grow &&
-                                (k < T || out_row);
-            double f[Q];
-            bool have = false, solid = false;
-            if (col_kind != 0 && row_on) {
-                have = true;
-                if (row_kind == 2) {
-#pragma unroll
-                    for (int i = 0; i < Q; ++i) f[i] = a.bc.e[i];
-                } else if (col_kind == 2) {
-#pragma unroll
-                    for (int i = 0; i < Q; ++i) f[i] = 0.0;
-                } else {
-                    int m = 0;
-                    if (xr + 1 >= a.mask_lo && xr + 1 < a.mask_hi) m = a.mask[L.at(xr + 1, yr)];
-                    solid = m != 0;
-                    if (m == 2) {
-                        // every neighbour is solid: the pulls are w, nothing to check, nothing to compute
-#pragma unroll
-                        for (int i = 0; i < Q; ++i) f[i] = a.bc.w[i];
-                    } else {
-                        // ---- pull ----------------------------------------------------------------
-                        if (k == 1) {
-                            int cw = xr - 1, ce = xr + 1;
-                            if (a.west == TB_EDGE_WRAP) { cw = tb_wrap(cw, lnx); ce = tb_wrap(ce, lnx); }
-                            const bool pulling = (T > 1) || a.pull;
-                            const long long bw = L.at(pulling ? cw + 1 : xr + 1, 0) - Layout::YO;
-                            const long long b0 = L.at(xr + 1, 0) - Layout::YO;
-                            const long long be = L.at(pulling ? ce + 1 : xr + 1, 0) - Layout::YO;
-                            const int r_m = pulling ? o_m : o_0, r_p = pulling ? o_p : o_0;
-                            const double* p = a.src;
-                            const long long pl = L.plane;
-                            // population i comes from column xr - c_ix, row yr - c_iy
-                            f[0] = TB_LD(p + 0 * pl + b0 + o_0, edge);
-                            f[1] = TB_LD(p + 1 * pl + bw + o_0, edge);
-                            f[2] = TB_LD(p + 2 * pl + b0 + r_m, edge);
-                            f[3] = TB_LD(p + 3 * pl + be + o_0, edge);
-                            f[4] = TB_LD(p + 4 * pl + b0 + r_p, edge);
-                            f[5] = TB_LD(p + 5 * pl + bw + r_m, edge);
-                            f[6] = TB_LD(p + 6 * pl + be + r_m, edge);
-                            f[7] = TB_LD(p + 7 * pl + be + r_p, edge);
-                            f[8] = TB_LD(p + 8 * pl + bw + r_p, edge);
-                        } else {
-                            const double* r = ring + (size_t)(k - 2) * TB_SLOTS * Q * B;
-                            const int sw = ((c - 1) & (TB_SLOTS - 1)) * Q * B, s0 = (c & (TB_SLOTS - 1)) * Q * B,
-                                      se = ((c + 1) & (TB_SLOTS - 1)) * Q * B;
-                            f[0] = r[s0 + 0 * B + tid];
-                            f[1] = r[sw + 1 * B + tid];
-                            f[2] = r[s0 + 2 * B + tid - 1];
-                            f[3] = r[se + 3 * B + tid];
-                            f[4] = r[s0 + 4 * B + tid + 1];
-                            f[5] = r[sw + 5 * B + tid - 1];
-                            f[6] = r[se + 6 * B + tid - 1];
-                            f[7] = r[se + 7 * B + tid + 1];
-                            f[8] = r[sw + 8 * B + tid + 1];
-                        }
-                        const bool rules = (T > 1) || a.pull;  // the first iteration has no boundary pass before it
-                        double rho_bc = 0.0, u_out = 0.0;
-                        if (!solid && rules) {
-                            // the reference's serial order: bottom, top, inlet, outlet
-                            if (wall_b) wall_bottom(f);
-                            if (wall_t) wall_top(f);
-                            if (a.bc.inlet && xr == 0) rho_bc = zou_he_inlet(f, a.bc.u_in);
-                            if (a.bc.outlet && xr == lnx - 1) u_out = zou_he_outlet(f);
-                        }
-                        (void)rho_bc;
-                        (void)u_out;
-                        if (rules) {
-#pragma unroll
-                            for (int i = 0; i < Q; ++i) bad[k - 1] |= unstable_value(f[i]);
-                        }
-                        if (solid) {
-#pragma unroll
-                            for (int i = 0; i < Q; ++i) f[i] = a.bc.w[i];
-                        } else {
-                            const Moments mo = moments(f);
-                            if (k == T && a.m_rho) {
-                                const long long g = (long long)c * ny + y;
-                                a.m_rho[g] = mo.rho;
-                                a.m_ux[g] = mo.ux;
-                                a.m_uy[g] = mo.uy;
-                            }
-                            if (FORCED)
-                                bgk_forced(f, mo, a.tau_inv, a.Fx, a.Fy, f);
-                            else
-                                bgk(f, mo, a.tau_inv, f);
-                        }
-                    }
-                    if (k == T && solid && a.m_rho) {  // include/LBMSolver.h:260-261; rho keeps the constructor's 1.0
-                        const long long g = (long long)c * ny + y;
-                        a.m_rho[g] = 1.0;
-                        a.m_ux[g] = 0.0;
-                        a.m_uy[g] = 0.0;
-                    }
-                }
+            for (; s + 1 < p1; s += 2) {
+                tb_step<T, B, FORCED, true>(a, r, ring, s, true, s >= m0 && s < m1, ca, cb, bad);
+                tb_step<T, B, FORCED, true>(a, r, ring, s + 1, true, s + 1 >= m0 && s + 1 < m1, cb, ca, bad);
             }
-            if (k < T) {
-                if (have) {
-                    double* w = ring + (size_t)(k - 1) * TB_SLOTS * Q * B + (c & (TB_SLOTS - 1)) * Q * B + tid;
-#pragma unroll
-                    for (int i = 0; i < Q; ++i) w[i * B] = f[i];
-                }
-                TB_SYNC();
-            } else if (have && a.write) {
-                // ---- the last stage: HBM, and the neighbours' ghost columns over NVLink ---------------
-                const long long o = L.at(c + 1, y);
-                // solid cells keep w for ever and are never stored -- except by the first iteration
-                // after an upload, whose destination buffer may hold anything there
-                if (!solid || (T == 1 && !a.pull)) {
-#pragma unroll
-                    for (int i = 0; i < Q; ++i) a.dst[i * L.plane + o] = f[i];
-                }
-                if (edge) {
-                    // Column lnx-1-d goes to the east neighbour's ghost column gx = -d.  What it needs of that column,
-                    // for a pass of depth halo_w: the populations moving towards it (1,5,8) always; the ones that stay in
-                    // the column (0,2,4) where it recomputes the column itself (d <= halo_w-2); the ones moving away
-                    // (3,6,7) where it also recomputes the column beyond (d <= halo_w-3).
-                    const int de = lnx - 1 - c, dw = c;
-                    if (a.px.peer_dst_east && de < a.halo_w) {
-                        double* q = a.px.peer_dst_east + L.at(-de, y);
-                        q[1 * L.plane] = f[1];
-                        q[5 * L.plane] = f[5];
-                        q[8 * L.plane] = f[8];
-                        if (de <= a.halo_w - 2) {
-                            q[0 * L.plane] = f[0];
-                            q[2 * L.plane] = f[2];
-                            q[4 * L.plane] = f[4];
-                        }
-                        if (de <= a.halo_w - 3) {
-                            q[3 * L.plane] = f[3];
-                            q[6 * L.plane] = f[6];
-                            q[7 * L.plane] = f[7];
-                        }
-                    }
-                    if (a.px.peer_dst_west && dw < a.halo_w) {
-                        double* q = a.px.peer_dst_west + L.at(lnx + 1 + dw, y);
-                        q[3 * L.plane] = f[3];
-                        q[6 * L.plane] = f[6];
-                        q[7 * L.plane] = f[7];
-                        if (dw <= a.halo_w - 2) {
-                            q[0 * L.plane] = f[0];
-                            q[2 * L.plane] = f[2];
-                            q[4 * L.plane] = f[4];
-                        }
-                        if (dw <= a.halo_w - 3) {
-                            q[1 * L.plane] = f[1];
-                            q[5 * L.plane] = f[5];
-                            q[8 * L.plane] = f[8];
-                        }
-                    }
-                }
+            if (s < p1) {
+                tb_step<T, B, FORCED, true>(a, r, ring, s, true, s >= m0 && s < m1, ca, cb, bad);
+                a_is_cur = false;
+                ++s;
             }
+            continue;
         }
+        if (a_is_cur) tb_step<T, B, FORCED, false>(a, r, ring, s, s < s_last, true, ca, cb, bad);
+        else tb_step<T, B, FORCED, false>(a, r, ring, s, s < s_last, true, cb, ca, bad);
+        a_is_cur = !a_is_cur;
+        ++s;
     }
 #pragma unroll
     for (int k = 0; k < T; ++k)
@@ -323,6 +538,7 @@ cudaError_t launch_tb(int depth, TbArgs a, bool p2p, cudaStream_t s);
 // 232-234), which are functions of the newest buffer alone.
 cudaError_t launch_macros_finish(const ObserveArgs& o, const double* m_rho, const double* m_ux, const double* m_uy,
                                  double* rho, double* ux, double* uy, cudaStream_t s);
+bool tb_worthwhile(const Layout& L);
 int tb_rows_per_block(int depth);
 size_t tb_shared_bytes(int depth);
 

@@ -131,6 +131,15 @@ int lbm_sync(lbm_handle h);
 
 /* IOManager::record_forces (LBMIO.h:114-168) for the current f_next: slab-local partial sums. */
 int lbm_get_forces(lbm_handle h, double* fx, double* fy);
+/* How the momentum-exchange sum over the link list is formed (LBMIO.h:123-160 adds the terms to one running sum
+ * per component, solid cells in (y, x) order, directions i = 1..8):
+ *   LBM_FORCES_ORDERED (default)  the same additions in the same order: the reference's bits, forces.csv byte for
+ *                                 byte; one thread per component, ~10 ns per link (81 us at 7904 links);
+ *   LBM_FORCES_TREE               a fixed parallel tree (warp shuffles + one shared-memory stage): deterministic from
+ *                                 launch to launch, ~3 us whatever the link count, equal to the ordered sum to
+ *                                 rounding (<= 1e-14 relative) -- for sampling the forces every (other) step. */
+enum { LBM_FORCES_ORDERED = 0, LBM_FORCES_TREE = 1 };
+int lbm_set_force_mode(lbm_handle h, int mode);
 /* Grid::check_stability (LBMGrid.h:285-317) of the current f_current, plus everything flagged
  * since the last initialise/upload.  *first_bad_step is the reference timestep or -1. */
 int lbm_check_stability(lbm_handle h, int* ok, int* first_bad_step);

@@ -35,7 +35,7 @@ FULL_CASES = {
 }
 SAMPLED_CASES = {
     "sampled_256x64": (O.Case(nx=256, ny=64, output_frequency=140), [1, 10, 100, 1000]),
-    "sampled_2048x512_default": (O.Case(), [1, 100, 300]),
+    "sampled_2048x512_default": (O.Case(), [1, 2, 10, 100, 300, 1000]),
 }
 
 

@@ -39,6 +39,26 @@ struct Slab {
     int cur = 0;
 };
 
+// k_wrap of the engine: periodic edges keep wrapped copies in the ghost ring (x first, then y with the ghost
+// columns, so that the corners come out right).
+void wrap_ghosts(Slab& s, bool wrap_x, bool wrap_y) {
+    const Layout& L = s.L;
+    double* f = s.f[s.cur].data();
+    for (int i = 0; i < Q; ++i) {
+        double* p = f + i * L.plane;
+        if (wrap_x)
+            for (int y = 0; y < L.ny; ++y) {
+                p[L.at(0, y)] = p[L.at(L.lnx, y)];
+                p[L.at(L.lnx + 1, y)] = p[L.at(1, y)];
+            }
+        if (wrap_y)
+            for (int gx = 0; gx < L.lnx + 2; ++gx) {
+                p[L.at(gx, -1)] = p[L.at(gx, L.ny - 1)];
+                p[L.at(gx, L.ny)] = p[L.at(gx, 0)];
+            }
+    }
+}
+
 template <int T, int B>
 void run_blocks(const TbArgs& a, int chunks) {
     using S = TbShape<T, B>;
@@ -144,6 +164,7 @@ int tb_emulate(double* state, const unsigned char* solid, int nx, int ny, double
                 if (s.mask[s.L.at(gx, y)])
                     for (int i = 0; i < Q; ++i) s.f[1][i * s.L.plane + s.L.at(gx, y)] = bc0.w[i];
     }
+    for (auto& s : slabs) wrap_ghosts(s, per_x && world == 1, per_y);
     int first_bad = 0x7fffffff;
     int iter = iter0;
     for (int p = 0; p < n_pass; ++p) {
@@ -188,6 +209,8 @@ int tb_emulate(double* state, const unsigned char* solid, int nx, int ny, double
                 a.xc = xc;
                 chunks = (lnx + xc - 1) / xc;
             }
+            tb_fill_offsets(a);
+            a.pf_dist = 1;
             run_pass(depth, B, a, chunks);
             if (!a.pull) {
                 // the engine's one-off launch after the first iteration: the buffer just read (an uploaded f_current may
@@ -199,6 +222,7 @@ int tb_emulate(double* state, const unsigned char* solid, int nx, int ny, double
             }
         }
         for (auto& s : slabs) s.cur ^= 1;
+        for (auto& s : slabs) wrap_ghosts(s, per_x && world == 1, per_y);  // the engine's k_wrap launches
         iter += depth;
     }
     for (int r = 0; r < world; ++r) {

@@ -21,7 +21,7 @@ def make(nx, ny, flags, **kw):
     return s
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("ny,tol", [(64, 2.0e-3), (128, 5.0e-4)])
 def test_shear_wave_decays_at_the_viscous_rate(ny, tol, variant):
     """u_x = u0 sin(2 pi y/ny) decays as exp(-nu k^2 t) (exact for Navier-Stokes; BGK adds an

@@ -27,17 +27,23 @@ def n_gpus():
     return torch.cuda.device_count()
 
 
+# kernel variant / pass depth: 1/1 = one iteration per launch pair (3-population halo), 2/d = temporally blocked
+# passes of depth d (wide halo stored by the pass itself, or sent by NCCL where forced)
+@pytest.mark.parametrize("variant,depth", [(2, 2), (2, 3), (2, 1), (1, 1)])
 @pytest.mark.parametrize("overlap", ["1", "0", "nccl"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("seed,case_name", [(0, "even"), (5, "even"), (5, "odd")])
-def test_slabs_match_single_rank_oracle(tmp_path, world, overlap, seed, case_name):
+def test_slabs_match_single_rank_oracle(tmp_path, world, overlap, seed, case_name, variant, depth):
     CASE = CASES[case_name]
     if n_gpus() < world:
         pytest.skip("needs %d GPUs" % world)
+    if variant == 2 and overlap == "0":
+        pytest.skip("the temporally blocked passes have one NCCL mode (in stream order)")
     steps = 37
     # "1": edge kernel + halo fused over peer memory when CUDA IPC is available (else the NCCL path);
     # "nccl": the overlapped NCCL send/recv path, forced; "0": exchange in stream order, no overlap
-    env = dict(os.environ, LBM_B200_OVERLAP="0" if overlap == "0" else "1", LBM_B200_P2P="0" if overlap == "nccl" else "1")
+    env = dict(os.environ, LBM_B200_OVERLAP="0" if overlap == "0" else "1", LBM_B200_P2P="0" if overlap == "nccl" else "1",
+               LBM_B200_VARIANT=str(variant), LBM_B200_TB_DEPTH=str(depth))
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         env.pop(k, None)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
@@ -67,8 +73,9 @@ def test_slabs_match_single_rank_oracle(tmp_path, world, overlap, seed, case_nam
     assert abs(float(parts[0]["maxvel"][0]) - o.max_velocity()) <= 1e-15
 
 
+@pytest.mark.parametrize("variant,depth", [(2, 2), (2, 3), (1, 1)])
 @pytest.mark.parametrize("p2p", ["1", "0"])
-def test_periodic_slabs_match_single_gpu(tmp_path, p2p):
+def test_periodic_slabs_match_single_gpu(tmp_path, p2p, variant, depth):
     """Periodic-x channel over 2 slabs: every rank has a neighbour on BOTH sides (the same peer), the
     situation of the middle ranks of a longer chain.  Reference: the same engine on one GPU."""
     if n_gpus() < 2:
@@ -76,7 +83,7 @@ def test_periodic_slabs_match_single_gpu(tmp_path, p2p):
     import lbm_b200
 
     steps, seed = 29, 3
-    env = dict(os.environ, LBM_B200_P2P=p2p)
+    env = dict(os.environ, LBM_B200_P2P=p2p, LBM_B200_VARIANT=str(variant), LBM_B200_TB_DEPTH=str(depth))
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         env.pop(k, None)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
@@ -99,3 +106,51 @@ def test_periodic_slabs_match_single_gpu(tmp_path, p2p):
     assert np.array_equal(parts[0]["g_rho"], rho) and np.array_equal(parts[0]["g_ux"], ux) and np.array_equal(parts[0]["g_uy"], uy)
     print("halo_p2p:", [int(p["halo_p2p"]) for p in parts])
     s.close()
+
+
+def _torchrun(world, script_args, env, port_base, timeout=600):
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(port_base + os.getpid() % 40), os.path.join(ROOT, "tests", "multi_gpu_worker.py")] + script_args
+    return subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout)
+
+
+@pytest.mark.parametrize("variant,depth", [(2, 2), (1, 1)])
+def test_observers_between_steps_with_skewed_ranks(tmp_path, variant, depth):
+    """rho / u are read in the middle of a run while the ranks are deliberately out of step (odd ranks sleep before
+    every observation, even ranks right after it): an observer that pulls from the previous buffer's ghost columns
+    must not see the halo of a neighbour that is already one pass ahead (the peer-store protocol has to
+    cover observers)."""
+    world = 2
+    if n_gpus() < world:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, LBM_B200_VARIANT=str(variant), LBM_B200_TB_DEPTH=str(depth))
+    r = _torchrun(world, [str(tmp_path), "0", "5", "even", "skewed"], env, 30050)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    CASE = CASES["even"]
+    o = util.oracle_with_state(CASE, util.random_state(CASE, 5))
+    parts = [np.load(tmp_path / ("skew%d.npz" % k)) for k in range(world)]
+    done = 0
+    for k, n in enumerate((1, 3, 4, 7, 2, 5)):
+        o.run(n)
+        done += n
+        for key, want in (("rho", o.rho), ("ux", o.ux), ("uy", o.uy)):
+            got = np.concatenate([p["%s_%d" % (key, k)] for p in parts], axis=1)
+            assert np.array_equal(got, want), "%s after %d iterations differs: max %.3e" % (key, done, np.abs(got - want).max())
+    got = np.concatenate([p["f_next"] for p in parts], axis=1)
+    assert np.array_equal(got, o.f_next[1:-1, 1:-1])
+
+
+def test_a_silent_neighbour_is_an_error_not_a_hang(tmp_path):
+    """Rank 1 stops stepping; rank 0's step kernels wait for its halo, run into the bound
+    (LBM_B200_HALO_TIMEOUT_MS) and every synchronising call on rank 0 returns LBM_ERR_NCCL within seconds."""
+    if n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, LBM_B200_HALO_TIMEOUT_MS="1500")
+    r = _torchrun(2, [str(tmp_path), "0", "0", "even", "silent"], env, 30100, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    res = np.load(tmp_path / "silent0.npz")
+    assert int(res["halo_p2p"]) == 0 or (int(res["code"]) == -3 and float(res["seconds"]) < 60.0), (int(res["code"]), float(res["seconds"]))
+    if int(res["halo_p2p"]):
+        assert b"timed out" in bytes(res["message"])

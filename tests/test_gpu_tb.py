@@ -131,3 +131,24 @@ def test_full_size_slab_two_passes():
     ofx, ofy = o.forces()
     assert fx == ofx and fy == ofy
     s.close()
+
+
+def test_tree_force_reduction_equals_the_ordered_sum_to_rounding():
+    """LBM_FORCES_TREE: the same link terms through a fixed parallel tree -- deterministic from run to run, within
+    1e-14 of the reference-ordered sum (relative to the largest partial sum), rows for every second iteration."""
+    case = O.Case(nx=384, ny=192, cylinder_radius=0.12, output_frequency=2, inlet_velocity=0.05)
+    runs = []
+    for tree in (0, 1, 1):
+        s = make(case, 2)
+        s.set_force_mode(tree)
+        rows, bad = s.run(80)
+        assert bad == -1 and len(rows) == 40
+        runs.append(rows)
+        s.close()
+    o = O.Oracle(case)
+    want, _ = o.run(80)
+    assert np.array_equal(runs[0], want)            # ordered mode: the reference's bits
+    assert np.array_equal(runs[1], runs[2])          # tree mode: deterministic
+    scale = np.abs(want[:, 1:3]).max()
+    assert np.abs(runs[1][:, 1:3] - want[:, 1:3]).max() <= 1e-14 * max(scale, 1.0)
+    assert np.array_equal(runs[1][:, 0], want[:, 0])
