@@ -106,7 +106,8 @@ EXPORTS = [
     "lbm_upload_f", "lbm_snapshot_begin", "lbm_snapshot_wait", "lbm_host_alloc", "lbm_host_free", "lbm_time_steps",
     "lbm_set_kernel_variant", "lbm_device_count", "lbm_get_counters", "lbm_event_record", "lbm_event_elapsed",
     "lbm_bootstrap_env", "lbm_set_params", "lbm_snapshot_begin_slot", "lbm_snapshot_wait_slot", "lbm_allreduce", "lbm_gather_macros",
-    "lbm_get_bulk_updates", "lbm_set_pass_depth", "lbm_set_force_mode",
+    "lbm_get_bulk_updates", "lbm_set_pass_depth", "lbm_set_force_mode", "lbm_snapshot_begin_slot2d", "lbm_host_register",
+    "lbm_host_unregister", "lbm_upload_f_next",
 ]
 
 _lib = None
@@ -165,6 +166,10 @@ def load():
     L.lbm_get_bulk_updates.argtypes = [H, LL]
     L.lbm_set_pass_depth.argtypes = [H, C.c_int]
     L.lbm_set_force_mode.argtypes = [H, C.c_int]
+    L.lbm_snapshot_begin_slot2d.argtypes = [H, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.lbm_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    L.lbm_host_unregister.argtypes = [C.c_void_p]
+    L.lbm_upload_f_next.argtypes = [H, C.c_void_p]
     for name in EXPORTS:
         if name != "lbm_last_error":
             getattr(L, name).restype = C.c_int
@@ -316,6 +321,13 @@ class Solver:
         i = self.info()
         assert a.shape == (i.local_ny + 2, i.local_nx + 2, 9), a.shape
         self._ck(load().lbm_upload_f(self._h, a.ctypes.data, iteration))
+
+    def upload_f_next(self, f_next: np.ndarray):
+        """Install caller-written f_next values (solid cells, S/N ghost rows, and the fluid cells' newest state)."""
+        a = np.ascontiguousarray(f_next, dtype=np.float64)
+        i = self.info()
+        assert a.shape == (i.local_ny + 2, i.local_nx + 2, 9), a.shape
+        self._ck(load().lbm_upload_f_next(self._h, a.ctypes.data))
 
     def snapshot_begin(self, rho, ux, uy):
         self._ck(load().lbm_snapshot_begin(self._h, rho.ctypes.data, ux.ctypes.data, uy.ctypes.data))

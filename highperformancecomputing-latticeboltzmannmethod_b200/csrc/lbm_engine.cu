@@ -86,6 +86,12 @@ struct lbm_solver {
     int lag = 1;
     double *d_mrho = nullptr, *d_mux = nullptr, *d_muy = nullptr;
     int macros_native_iter = -1;
+    long long* d_custom_off = nullptr;  // lbm_upload_f_next: (offset, value) of the solid / ghost-row populations written
+    double* d_custom_val = nullptr;
+    int n_custom = 0;
+    bool custom_pending = false;  // ... to be installed right after the next iteration (see lbm_upload_f_next)
+    bool custom_state = false;  // the caller wrote f_next (solid / ghost-row values may no longer be the constants the
+                                // temporally blocked passes build in): one-iteration kernels from then on
     int force_tree = 0;      // LBM_FORCES_TREE: fixed parallel reduction tree instead of the reference's serial order
     bool emit_last = false;  // lbm_run: the last pass of the call emits (the caller will look at the fields)
     int mask_lo = 0, mask_hi = 0;  // padded columns gx in [lo, hi) hold solid cells
@@ -950,6 +956,11 @@ int step_one(lbm_handle h) {
         h->pending.push_back({h->iter, slot});
     }
 
+    if (h->custom_pending) {
+        CU(h, launch_scatter(h->d_custom_off, h->d_custom_val, h->n_custom, h->f[0], h->f[1], h->stream));
+        h->launches += 1;
+        h->custom_pending = false;
+    }
     h->cur ^= 1;
     h->prev_is_next = h->cur_is_next;
     h->cur_is_next = true;
@@ -1034,7 +1045,7 @@ int check_pending(lbm_handle h) {
         return LBM_OK;
     }
     { int rc_ = join_halo(h); if (rc_) return rc_; }
-    if (h->variant == BULK_TB) {
+    if (h->variant == BULK_TB && !h->custom_state) {
         TbArgs t = tb_args(h, h->f[h->cur], h->f[h->cur ^ 1], h->iter - 1, 0);
         CU(h, launch_tb(1, t, false, h->stream));
         h->launches += 1;
@@ -1272,7 +1283,7 @@ int lbm_destroy(lbm_handle h) {
     cudaFree(h->d_first_bad); cudaFree(h->d_forces); cudaFree(h->d_maxbits);
     cudaFree(h->d_red); cudaFree(h->d_gather); cudaFree(h->d_first_bad_all);
     cudaFree(h->d_flags); cudaFree(h->d_blocks_done); cudaFree(h->d_status);
-    cudaFree(h->d_mrho); cudaFree(h->d_mux); cudaFree(h->d_muy);
+    cudaFree(h->d_mrho); cudaFree(h->d_mux); cudaFree(h->d_muy); cudaFree(h->d_custom_off); cudaFree(h->d_custom_val);
     cudaFree(h->d_cols); cudaFree(h->d_fills); cudaFree(h->d_links_rev); cudaFree(h->d_links_nat); cudaFree(h->d_ring_out);
     if (h->ev_macros) cudaEventDestroy(h->ev_macros);
     if (h->ev_snapshot) cudaEventDestroy(h->ev_snapshot);
@@ -1348,6 +1359,8 @@ int lbm_initialise(lbm_handle h, double inlet_u) {
     h->macros_valid = false;
     h->lag = 1;
     h->macros_native_iter = -1;
+    h->custom_state = false;
+    h->custom_pending = false;
     h->pending.clear();
     h->force_log.clear();
     if (h->p2p) return slab_barrier(h);  // every slab initialised before any neighbour pushes a halo into it
@@ -1360,7 +1373,7 @@ int lbm_step(lbm_handle h, int n_steps) {
     if (n_steps < 0) return fail(h, LBM_ERR_INVALID, "n_steps < 0");
     CU(h, cudaSetDevice(h->device));
     if (h->halo_failed) return halo_status(h);
-    if (h->aa || h->variant != BULK_TB) {
+    if (h->aa || h->variant != BULK_TB || h->custom_state) {
         for (int k = 0; k < n_steps; ++k) {
             int rc = step_one(h);
             if (rc) return rc;
@@ -1606,6 +1619,53 @@ int lbm_upload_f(lbm_handle h, const double* aos, int iteration) {
     return LBM_OK;
 }
 
+int lbm_upload_f_next(lbm_handle h, const double* aos) {
+    CHECK_H(h);
+    if (!aos) return fail(h, LBM_ERR_INVALID, "null argument");
+    if (!h->initialised) return fail(h, LBM_ERR_INVALID, "lbm_initialise or lbm_upload_f first");
+    if (h->aa) return fail(h, LBM_ERR_INVALID, "the in-place variant keeps no separate f_next to write into");
+    CU(h, cudaSetDevice(h->device));
+    // What a write to f_next can mean at an iteration boundary of the reference (include/LBMSolver.h:48-64): its
+    // streaming has already consumed f_next and the next collision overwrites every FLUID cell, so fluid values are
+    // dead; the values of solid cells and of the S/N ghost rows live on -- the NEXT iteration's streaming, and every
+    // later one, pulls them.  The engine's fused step still owes the streaming of the iteration just finished (it
+    // must pull the OLD values), so the new ones are installed in both buffers right after the next step.
+    const Layout& L = h->L;
+    const size_t tnx = (size_t)L.lnx + 2;
+    std::vector<long long> off;
+    std::vector<double> val;
+    auto take = [&](int gx, int y) {
+        const double* src = aos + ((size_t)(y + 1) * tnx + gx) * Q;
+        for (int i = 0; i < Q; ++i) {
+            off.push_back((long long)i * L.plane + L.at(gx, y));
+            val.push_back(src[i]);
+        }
+    };
+    for (int y = 0; y < L.ny; ++y)
+        for (int gx = 1; gx <= L.lnx; ++gx)
+            if (h->h_mask[L.at(gx, y)]) take(gx, y);
+    if (!h->periodic_y)
+        for (int gx = 0; gx < L.lnx + 2; ++gx) {
+            take(gx, -1);
+            take(gx, L.ny);
+        }
+    CU(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_custom_off);
+    cudaFree(h->d_custom_val);
+    h->d_custom_off = nullptr;
+    h->d_custom_val = nullptr;
+    h->n_custom = (int)off.size();
+    if (h->n_custom) {
+        CU(h, cudaMalloc(&h->d_custom_off, off.size() * sizeof(long long)));
+        CU(h, cudaMalloc(&h->d_custom_val, val.size() * sizeof(double)));
+        CU(h, cudaMemcpy(h->d_custom_off, off.data(), off.size() * sizeof(long long), cudaMemcpyHostToDevice));
+        CU(h, cudaMemcpy(h->d_custom_val, val.data(), val.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    h->custom_pending = h->n_custom > 0;
+    h->custom_state = true;
+    return LBM_OK;
+}
+
 int lbm_snapshot_begin(lbm_handle h, double* rho, double* ux, double* uy) {
     CHECK_H(h);
     CU(h, cudaSetDevice(h->device));
@@ -1633,6 +1693,29 @@ int lbm_snapshot_begin_slot(lbm_handle h, int slot, double* rho, double* ux, dou
     return LBM_OK;
 }
 
+// The same into a wider host image: row y of this slab lands at rho + y*row_pitch (doubles), i.e. the caller passes
+// the address of its slab's first column inside an image of the whole channel that several slabs fill side by side.
+int lbm_snapshot_begin_slot2d(lbm_handle h, int slot, double* rho, double* ux, double* uy, size_t row_pitch) {
+    CHECK_H(h);
+    if (slot < 0 || slot >= LBM_SNAPSHOT_SLOTS) return fail(h, LBM_ERR_INVALID, "snapshot slot out of range");
+    if (row_pitch < (size_t)h->L.lnx) return fail(h, LBM_ERR_INVALID, "row pitch smaller than the slab width");
+    CU(h, cudaSetDevice(h->device));
+    if (!h->ev_slot[slot]) CU(h, cudaEventCreateWithFlags(&h->ev_slot[slot], cudaEventDisableTiming));
+    int rc = ensure_macros(h);
+    if (rc) return rc;
+    CU(h, cudaEventRecord(h->ev_macros, h->stream));
+    CU(h, cudaStreamWaitEvent(h->copy_stream, h->ev_macros, 0));
+    const size_t w = (size_t)h->L.lnx * sizeof(double), dp = row_pitch * sizeof(double);
+    double* dst[3] = {rho, ux, uy};
+    double* src[3] = {h->d_rho, h->d_ux, h->d_uy};
+    for (int k = 0; k < 3; ++k)
+        if (dst[k]) CU(h, cudaMemcpy2DAsync(dst[k], dp, src[k], w, w, h->L.ny, cudaMemcpyDeviceToHost, h->copy_stream));
+    CU(h, cudaEventRecord(h->ev_snapshot, h->copy_stream));
+    h->snapshot_pending = true;
+    CU(h, cudaEventRecord(h->ev_slot[slot], h->copy_stream));
+    return LBM_OK;
+}
+
 // Safe to call from a second host thread (an output writer): touches nothing but the event.
 int lbm_snapshot_wait_slot(lbm_handle h, int slot) {
     CHECK_H(h);
@@ -1655,6 +1738,18 @@ int lbm_host_alloc(void** ptr, size_t bytes) {
     if (!ptr) return LBM_ERR_INVALID;
     cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocDefault);
     if (e != cudaSuccess) return fail(nullptr, e == cudaErrorMemoryAllocation ? LBM_ERR_NOMEM : LBM_ERR_CUDA, cudaGetErrorString(e));
+    return LBM_OK;
+}
+
+int lbm_host_register(void* ptr, size_t bytes) {
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) return fail(nullptr, LBM_ERR_CUDA, cudaGetErrorString(e));
+    return LBM_OK;
+}
+
+int lbm_host_unregister(void* ptr) {
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) return fail(nullptr, LBM_ERR_CUDA, cudaGetErrorString(e));
     return LBM_OK;
 }
 

@@ -587,9 +587,25 @@ __global__ void __launch_bounds__(256) k_import_f(const double* __restrict__ aos
     }
 }
 
+// Caller-written f_next values of solid cells / ghost rows (lbm_upload_f_next): a compact (offset, value) list into
+// both population buffers.
+__global__ void __launch_bounds__(256) k_scatter(const long long* __restrict__ off, const double* __restrict__ val, int n,
+                                                 double* __restrict__ f0, double* __restrict__ f1) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    f0[off[k]] = val[k];
+    if (f1) f1[off[k]] = val[k];
+}
+
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace
+
+cudaError_t launch_scatter(const long long* off, const double* val, int n, double* f0, double* f1, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    k_scatter<<<cdiv(n, 256), 256, 0, s>>>(off, val, n, f0, f1);
+    return cudaGetLastError();
+}
 
 // ------------------------------------------------------------------------------------------
 cudaError_t launch_bulk(int variant, bool pull, const StepArgs& a, cudaStream_t s, int x_begin, int x_end) {

@@ -33,6 +33,8 @@ class Grid {
         unsigned char id[128];
         int local = 0;
         check_create(lbm_bootstrap_env(&rank_, &world_, &local, id));
+        if (world_ > 1)  // a tag every slab process of THIS launch shares and no other launch does (the NCCL id is random)
+            for (int k = 0; k < 128; ++k) job_tag_ = job_tag_ * 1099511628211ULL ^ id[k];
         int ndev = 0;
         lbm_device_count(&ndev);
         const int device = ndev > 0 ? local % ndev : 0;
@@ -68,13 +70,28 @@ class Grid {
         f_dirty_ = true;
         return cache_f_[LBM_F_CURRENT][f_index(x, y, i)];
     }
+    // Writable view of f_next (reference :119-121).  As in the reference, a write at an iteration boundary matters only
+    // in solid cells and S/N ghost rows (the next collision overwrites every fluid cell): lbm_upload_f_next.
+    double& f_next(int x, int y, int i) {
+        fetch(LBM_F_NEXT);
+        fn_dirty_ = true;
+        return cache_f_[LBM_F_NEXT][f_index(x, y, i)];
+    }
     const double* f_current_ptr(int x, int y) const { return &f_current(x, y, 0); }
     const double* f_next_ptr(int x, int y) const { return &f_next(x, y, 0); }
+    double* f_current_ptr(int x, int y) { return &f_current(x, y, 0); }  // (reference :116, :120: mutable pointers)
+    double* f_next_ptr(int x, int y) { return &f_next(x, y, 0); }
 
     // ---- macroscopic fields and mask, interior coordinates (reference :124-129, :145) ----
     const double& rho(int x, int y) const { return macros()[0][m_index(x, y)]; }
     const double& ux(int x, int y) const { return macros()[1][m_index(x, y)]; }
     const double& uy(int x, int y) const { return macros()[2][m_index(x, y)]; }
+    // Writable macroscopic fields (reference :124-126).  The reference's next collision overwrites them in every fluid
+    // cell and its boundary pass in the inlet / outlet / solid cells, so a write is visible to the output routines until
+    // the run advances -- exactly that is kept: the edit lives in the host-side view and is dropped by the next advance.
+    double& rho(int x, int y) { return const_cast<std::vector<double>*>(macros())[0][m_index(x, y)]; }
+    double& ux(int x, int y) { return const_cast<std::vector<double>*>(macros())[1][m_index(x, y)]; }
+    double& uy(int x, int y) { return const_cast<std::vector<double>*>(macros())[2][m_index(x, y)]; }
     bool is_solid(int x, int y) const {
         if (solid_.empty()) {
             solid_.resize((size_t)local_nx() * local_ny());
@@ -139,6 +156,7 @@ class Grid {
 
     // ---- engine access for Solver / IOManager ----
     lbm_handle handle() const { return h_; }
+    unsigned long long job_tag() const { return job_tag_; }
     const SimulationParams& params() const { return params_; }
     void adopt(const SimulationParams& params) {
         lbm_params c = params.to_c();
@@ -208,14 +226,19 @@ class Grid {
 
     void invalidate() const {
         have_f_[0] = have_f_[1] = have_m_ = false;
-        f_dirty_ = false;
+        f_dirty_ = fn_dirty_ = false;
     }
     void flush_edits() {
-        if (!f_dirty_) return;
-        lbm_info now;
-        check(lbm_get_info(h_, &now));
-        check(lbm_upload_f(h_, cache_f_[LBM_F_CURRENT].data(), now.iteration));
-        f_dirty_ = false;
+        if (f_dirty_) {
+            lbm_info now;
+            check(lbm_get_info(h_, &now));
+            check(lbm_upload_f(h_, cache_f_[LBM_F_CURRENT].data(), now.iteration));
+            f_dirty_ = false;
+        }
+        if (fn_dirty_) {
+            check(lbm_upload_f_next(h_, cache_f_[LBM_F_NEXT].data()));
+            fn_dirty_ = false;
+        }
     }
     const std::vector<double>& fetch(int which) const {
         if (!have_f_[which]) {
@@ -239,12 +262,13 @@ class Grid {
     lbm_handle h_ = nullptr;
     lbm_info info_{};
     int rank_ = 0, world_ = 1;
+    unsigned long long job_tag_ = 1469598103934665603ULL;
     mutable std::vector<double> cache_f_[2];
     mutable std::vector<double> cache_m_[3];
     mutable std::vector<unsigned char> solid_;
     mutable bool have_f_[2] = {false, false};
     mutable bool have_m_ = false;
-    mutable bool f_dirty_ = false;
+    mutable bool f_dirty_ = false, fn_dirty_ = false;
 };
 
 }  // namespace LBM

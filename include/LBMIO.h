@@ -15,7 +15,13 @@
 //     reference's iostream writer needs ~2 s for a 50 MB frame).
 #pragma once
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <condition_variable>
 #include <cstdint>
@@ -26,6 +32,7 @@
 #include <functional>
 #include <iomanip>
 #include <iostream>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -372,46 +379,132 @@ class IOManager {
 // frame k is copied into image k%2 on the engine's copy stream while the compute stream moves
 // on, and a writer thread formats it once its copy has landed.  submit() blocks only when both
 // images are still being written (the ASCII format, not the GPU, is then the bottleneck).
+// One image of the whole channel in POSIX shared memory, page-locked in every slab process: each GPU copies its own
+// columns into it (lbm_snapshot_begin_slot2d), nobody gathers anything.  Two slots; a small header of lock-free
+// counters says which frame each slab has delivered into a slot and which frames rank 0 has written.
+class SharedFrameImage {
+   public:
+    static constexpr int kMaxSlabs = 64;
+    struct Header {
+        std::atomic<int64_t> magic;
+        std::atomic<int64_t> attached;               // slab processes that have mapped the segment
+        std::atomic<int64_t> written;                // frames rank 0 has finished writing
+        std::atomic<int64_t> ready[2][kMaxSlabs];    // ready[slot][r] = k+1: slab r's part of frame k is in the slot
+    };
+
+    SharedFrameImage(const Grid& grid) : grid_(grid) {
+        n_ = (size_t)grid.global_nx() * grid.global_ny();
+        bytes_ = sizeof(Header) + 2 * 3 * n_ * sizeof(double);
+        bytes_ = (bytes_ + 4095) / 4096 * 4096;
+        char name[96];
+        std::snprintf(name, sizeof(name), "/lbm_b200_frames_%016llx", grid.job_tag());
+        name_ = name;
+        int fd = -1;
+        if (grid.mpi_rank() == 0) {
+            shm_unlink(name_.c_str());
+            fd = shm_open(name_.c_str(), O_CREAT | O_EXCL | O_RDWR, 0600);
+            if (fd < 0 || ftruncate(fd, (off_t)bytes_) != 0) throw std::runtime_error("lbm_b200: cannot create shared frame image " + name_);
+        } else {
+            for (int tries = 0; tries < 12000 && fd < 0; ++tries) {  // up to 60 s
+                fd = shm_open(name_.c_str(), O_RDWR, 0600);
+                struct stat st;
+                if (fd >= 0 && (fstat(fd, &st) != 0 || (size_t)st.st_size < bytes_)) {
+                    close(fd);
+                    fd = -1;
+                }
+                if (fd < 0) usleep(5000);
+            }
+            if (fd < 0) throw std::runtime_error("lbm_b200: timed out waiting for shared frame image " + name_);
+        }
+        base_ = mmap(nullptr, bytes_, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        close(fd);
+        if (base_ == MAP_FAILED) throw std::runtime_error("lbm_b200: mmap of the shared frame image failed");
+        hdr_ = static_cast<Header*>(base_);
+        if (grid.mpi_rank() == 0) {
+            hdr_->attached.store(0);
+            hdr_->written.store(0);
+            for (auto& slot : hdr_->ready)
+                for (auto& r : slot) r.store(0);
+            hdr_->magic.store(kMagic, std::memory_order_release);
+        } else {
+            for (int tries = 0; hdr_->magic.load(std::memory_order_acquire) != kMagic; ++tries) {
+                if (tries > 12000) throw std::runtime_error("lbm_b200: shared frame image never initialised");
+                usleep(5000);
+            }
+        }
+        registered_ = lbm_host_register(base_, bytes_) == LBM_OK;  // pageable memory still works, only synchronously
+        hdr_->attached.fetch_add(1);
+    }
+    ~SharedFrameImage() {
+        if (!base_ || base_ == MAP_FAILED) return;
+        if (grid_.mpi_rank() == 0) {
+            for (int tries = 0; hdr_->attached.load() < grid_.mpi_size() && tries < 2000; ++tries) usleep(5000);
+            shm_unlink(name_.c_str());
+        }
+        if (registered_) lbm_host_unregister(base_);
+        munmap(base_, bytes_);
+    }
+    Header* header() { return hdr_; }
+    double* field(int slot, int k) { return reinterpret_cast<double*>(static_cast<char*>(base_) + sizeof(Header)) + ((size_t)slot * 3 + k) * n_; }
+    size_t cells() const { return n_; }
+
+   private:
+    static constexpr int64_t kMagic = 0x4c424d4652414d45LL;
+    const Grid& grid_;
+    std::string name_;
+    void* base_ = nullptr;
+    Header* hdr_ = nullptr;
+    size_t n_ = 0, bytes_ = 0;
+    bool registered_ = false;
+};
+
 class FrameWriter {
    public:
     explicit FrameWriter(const Grid& grid, bool binary = false) : grid_(grid), binary_(binary) {}
     ~FrameWriter() { finish(); }
 
+    // Returns as soon as the device-side snapshot is queued: the D2H copies run on the engine's copy stream, the
+    // formatting and the file write on a host thread, while the caller keeps stepping.  Multi-slab jobs: every slab
+    // process calls this; its GPU fills its own columns of the shared image and rank 0's thread writes the file when
+    // all parts have arrived -- no collective, no gather through rank 0's GPU.
     void submit(int timestep) {
-        const int slot = (int)(submitted_ % 2);
-        const size_t n = (size_t)grid_.global_nx() * grid_.global_ny();
-        {
-            std::unique_lock<std::mutex> lk(m_);
-            cv_.wait(lk, [&] { return !busy_[slot]; });
-        }
+        const int64_t k = (int64_t)submitted_;
+        const int slot = (int)(k % 2);
         const bool root = grid_.mpi_rank() == 0;
-        if (root && !image_[slot]) {
-            void* p = nullptr;
-            grid_.check(lbm_host_alloc(&p, 3 * n * sizeof(double)));
-            image_[slot] = static_cast<double*>(p);
-        }
-        double* rho = root ? image_[slot] : nullptr;
-        double* ux = root ? image_[slot] + n : nullptr;
-        double* uy = root ? image_[slot] + 2 * n : nullptr;
-        bool wait_slot = false;
-        if (grid_.mpi_size() == 1) {
-            grid_.check(lbm_snapshot_begin_slot(grid_.handle(), slot, rho, ux, uy));  // returns at once
-            wait_slot = true;
+        const bool multi = grid_.mpi_size() > 1;
+        if (multi) {
+            if (grid_.mpi_size() > SharedFrameImage::kMaxSlabs) throw std::runtime_error("lbm_b200: too many slabs for the shared frame image");
+            if (!shared_) shared_ = std::make_unique<SharedFrameImage>(grid_);
+            // the slot is free once rank 0 has written frame k-2 (back-pressure only when the writer is two frames behind)
+            while (shared_->header()->written.load(std::memory_order_acquire) < k - 1) usleep(200);
+            const size_t pitch = (size_t)grid_.global_nx();
+            grid_.check(lbm_snapshot_begin_slot2d(grid_.handle(), slot, shared_->field(slot, 0) + grid_.x_start(),
+                                                  shared_->field(slot, 1) + grid_.x_start(), shared_->field(slot, 2) + grid_.x_start(), pitch));
         } else {
-            grid_.check(lbm_gather_macros(grid_.handle(), rho, ux, uy));  // collective, synchronous
+            const size_t n = (size_t)grid_.global_nx() * grid_.global_ny();
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return !busy_[slot]; });
+            }
+            if (!image_[slot]) {
+                void* p = nullptr;
+                grid_.check(lbm_host_alloc(&p, 3 * n * sizeof(double)));
+                image_[slot] = static_cast<double*>(p);
+            }
+            grid_.check(lbm_snapshot_begin_slot(grid_.handle(), slot, image_[slot], image_[slot] + n, image_[slot] + 2 * n));
         }
         ++submitted_;
-        if (!root) return;
         {
             std::lock_guard<std::mutex> lk(m_);
             busy_[slot] = true;
-            jobs_.push_back({timestep, slot, wait_slot});
+            jobs_.push_back({timestep, slot, k});
         }
         if (!thread_.joinable()) thread_ = std::thread([this] { loop(); });
         cv_.notify_all();
+        (void)root;
     }
 
-    // Blocks until every submitted frame is on disk.
+    // Blocks until every submitted frame is on disk (rank 0) / delivered (other slabs).
     void finish() {
         {
             std::lock_guard<std::mutex> lk(m_);
@@ -420,6 +513,11 @@ class FrameWriter {
         cv_.notify_all();
         if (thread_.joinable()) thread_.join();
         stop_ = false;
+        if (shared_) {
+            // nobody unmaps before rank 0 has written the last frame out of the shared image
+            while (shared_->header()->written.load(std::memory_order_acquire) < (int64_t)submitted_) usleep(500);
+            shared_.reset();
+        }
         for (double*& p : image_)
             if (p) {
                 lbm_host_free(p);
@@ -432,7 +530,7 @@ class FrameWriter {
    private:
     struct Job {
         int timestep, slot;
-        bool wait_slot;
+        int64_t index;
     };
     void loop() {
         for (;;) {
@@ -444,13 +542,32 @@ class FrameWriter {
                 j = jobs_.front();
                 jobs_.pop_front();
             }
-            if (j.wait_slot) lbm_snapshot_wait_slot(grid_.handle(), j.slot);
+            lbm_snapshot_wait_slot(grid_.handle(), j.slot);  // this slab's D2H copies of the frame have landed
             const size_t n = (size_t)grid_.global_nx() * grid_.global_ny();
-            const double* img = image_[j.slot];
-            if (binary_)
-                IOManager::write_vtk_arrays_binary(img + n, img + 2 * n, img, grid_.global_nx(), grid_.global_ny(), j.timestep);
-            else
-                IOManager::write_vtk_arrays(img + n, img + 2 * n, img, grid_.global_nx(), grid_.global_ny(), j.timestep);
+            const double *rho, *ux, *uy;
+            bool write = true;
+            if (shared_) {
+                auto* hdr = shared_->header();
+                hdr->ready[j.slot][grid_.mpi_rank()].store(j.index + 1, std::memory_order_release);
+                write = grid_.mpi_rank() == 0;
+                if (write)
+                    for (int r = 0; r < grid_.mpi_size(); ++r)
+                        while (hdr->ready[j.slot][r].load(std::memory_order_acquire) < j.index + 1) usleep(100);
+                rho = shared_->field(j.slot, 0);
+                ux = shared_->field(j.slot, 1);
+                uy = shared_->field(j.slot, 2);
+            } else {
+                rho = image_[j.slot];
+                ux = image_[j.slot] + n;
+                uy = image_[j.slot] + 2 * n;
+            }
+            if (write) {
+                if (binary_)
+                    IOManager::write_vtk_arrays_binary(ux, uy, rho, grid_.global_nx(), grid_.global_ny(), j.timestep);
+                else
+                    IOManager::write_vtk_arrays(ux, uy, rho, grid_.global_nx(), grid_.global_ny(), j.timestep);
+                if (shared_) shared_->header()->written.store(j.index + 1, std::memory_order_release);
+            }
             {
                 std::lock_guard<std::mutex> lk(m_);
                 busy_[j.slot] = false;
@@ -463,6 +580,7 @@ class FrameWriter {
     const Grid& grid_;
     bool binary_ = false;
     double* image_[2] = {nullptr, nullptr};
+    std::unique_ptr<SharedFrameImage> shared_;
     bool busy_[2] = {false, false};
     std::deque<Job> jobs_;
     std::mutex m_;

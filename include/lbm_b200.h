@@ -169,6 +169,15 @@ int lbm_download_solid(lbm_handle h, unsigned char* mask);
  * the next lbm_step will execute. */
 int lbm_upload_f(lbm_handle h, const double* f_current_aos_padded, int iteration);
 
+/* Grid::f_next written by the caller (LBMGrid.h:119-121 hands out a mutable reference).  At an iteration boundary of
+ * the reference its streaming has already consumed f_next and the next collision overwrites every fluid cell, so
+ * only the values of SOLID cells and of the S/N GHOST ROWS (corners included) live on: the next iteration's streaming
+ * and every later one pull them.  Exactly those values are taken from the image (fluid cells and the W/E ghost
+ * columns, which the exchange rewrites every step, are ignored) and take effect with the next iteration, as in the
+ * reference; lbm_download_f shows them after that iteration.  From this call on the handle runs the one-iteration
+ * kernels: the temporally blocked passes build the default constants in.  Single-rank semantics per slab. */
+int lbm_upload_f_next(lbm_handle h, const double* f_next_aos_padded);
+
 /* ---- async output: replaces the MPI gathers of Solver::write_vtk_frame (LBMSolver.h:269-362)
  * and IOManager::gather_and_reconstruct_field (LBMIO.h:225-300).  Snapshots rho/ux/uy of the
  * current state into caller-owned host buffers (pinned via lbm_host_alloc for true overlap) on
@@ -181,6 +190,13 @@ int lbm_snapshot_wait(lbm_handle h);
 #define LBM_SNAPSHOT_SLOTS 4
 int lbm_snapshot_begin_slot(lbm_handle h, int slot, double* rho, double* ux, double* uy);
 int lbm_snapshot_wait_slot(lbm_handle h, int slot);
+/* ... into an image of the WHOLE channel that the slabs of a job fill side by side (rows of row_pitch doubles;
+ * pass the address of this slab's first column): with the image in memory shared by the slab processes and
+ * registered with lbm_host_register, every GPU writes its part by itself, asynchronously -- no gather, no collective
+ * (the reference funnels every frame through MPI_Gatherv to rank 0, LBMSolver.h:289-337). */
+int lbm_snapshot_begin_slot2d(lbm_handle h, int slot, double* rho, double* ux, double* uy, size_t row_pitch);
+int lbm_host_register(void* ptr, size_t bytes); /* cudaHostRegister: page-lock memory the caller mapped (e.g. shm) */
+int lbm_host_unregister(void* ptr);
 int lbm_host_alloc(void** ptr, size_t bytes); /* cudaHostAlloc */
 int lbm_host_free(void* ptr);
 

@@ -101,14 +101,27 @@ def test_driver_reports_instability_like_the_reference(exe, tmp_path):
     assert open(tmp_path / "forces.csv").read() == O.format_forces_csv(rows)
 
 
-def test_driver_two_slabs(exe, tmp_path):
+@pytest.mark.parametrize("extra", [(), ("--sync-vtk",)])
+def test_driver_two_slabs(exe, tmp_path, extra):
+    """Two x-slabs, one process per GPU.  Async VTK (default): every GPU copies its own columns into one page-locked
+    image in shared memory and rank 0's writer thread formats the file -- no gather; --sync-vtk: the NCCL gather."""
     import torch
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     launcher = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                 "--master-port", str(29700 + os.getpid() % 200), "--no-python"]
-    out = run_driver(exe, tmp_path, launcher=launcher)
+    out = run_driver(exe, tmp_path, extra=extra, launcher=launcher)
+    # the VTK frames: rho / u of the two slabs side by side, byte for byte what the 1-rank oracle gives
+    o2 = O.Oracle(CASE)
+    want_frames = {}
+    for t in range(STEPS):
+        o2.run(1)
+        if t >= 200 and t % CASE.output_frequency == 0:
+            want_frames[t] = vtk_text(o2.rho.copy(), o2.ux.copy(), o2.uy.copy(), t)
+    assert sorted(os.listdir(tmp_path / "vtk_output")) == ["lbm_%06d.vtk" % t for t in sorted(want_frames)]
+    for t, want in want_frames.items():
+        assert open(tmp_path / "vtk_output" / ("lbm_%06d.vtk" % t), "rb").read() == want, t
     # per-slab partial force sums are added by NCCL: equal to the serial sum to rounding, so
     # compare numerically at the file's own 8 decimals, everything else byte for byte
     o = O.Oracle(CASE)

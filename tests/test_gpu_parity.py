@@ -266,3 +266,33 @@ def test_degenerate_lattices(nx, ny, aa):
     if bad == -1:
         util.compare_state(s, o, "%dx%d aa=%d" % (nx, ny, aa), exact=True, macros_exact=(aa == 0))
     s.close()
+
+
+def test_written_f_next_of_solid_cells_and_ghost_rows_takes_effect_like_in_the_reference():
+    """Grid::f_next is writable in the reference (include/LBMGrid.h:119-121).  At an iteration boundary a write only
+    matters in solid cells and S/N ghost rows (every later streaming pulls them); fluid cells are overwritten by the
+    next collision.  lbm_upload_f_next reproduces exactly that, bit for bit."""
+    case = CASES["96x48"]
+    s, o = make_solver(case, 2), O.Oracle(case)
+    s.step(6)
+    o.run(6)
+    fn = s.f_next()
+    assert np.array_equal(fn, o.f_next)
+    ys, xs = np.nonzero(o.solid)
+    edit = fn.copy()
+    edit[ys + 1, xs + 1, :] *= 1.0 + 0.01 * np.arange(9)          # every solid cell
+    edit[0, :, :] *= 0.97                                          # S ghost row (and its corners)
+    edit[-1, 5:20, 3] += 0.002                                     # part of the N ghost row
+    edit[10:20, 30:40, :] = 123.0                                  # fluid cells: dead values, must change nothing
+    fluid_block_is_fluid = not o.solid[9:19, 29:39].any()
+    s.upload_f_next(edit)
+    of = o.f_next
+    of[ys + 1, xs + 1, :] = edit[ys + 1, xs + 1, :]
+    of[0, :, :] = edit[0, :, :]
+    of[-1, :, :] = edit[-1, :, :]
+    assert fluid_block_is_fluid
+    for n in (1, 1, 2, 9):
+        s.step(n)
+        o.run(n)
+        util.compare_state(s, o, "after writing f_next +%d" % n, exact=True)
+    s.close()
