@@ -27,6 +27,7 @@
 #include <cstdint>
 
 #include "lbm_cell.cuh"
+#include "lbm_device.cuh"
 #include "lbm_kernels.cuh"
 #include "lbm_launch.cuh"
 
@@ -264,7 +265,9 @@ __global__ void __launch_bounds__(128) k_aa_fix_odd(AaArgs a, BcArgs b, const in
         for (int i = 0; i < Q; ++i) {
             out[i] = f[i];
             const int tx = c.x + cxi(i), ty = y + cyi(i);
-            const bool ok = (open_x || (tx >= 0 && tx < L.lnx)) && (open_y || (ty >= 0 && ty < L.ny));
+            // open_x: bit 0 = the west edge is open (periodic, or a neighbouring slab takes what is pushed across it), bit 1 = east
+            const bool ok_x = tx < 0 ? (open_x & 1) != 0 : (tx >= L.lnx ? (open_x & 2) != 0 : true);
+            const bool ok = ok_x && (open_y || (ty >= 0 && ty < L.ny));
             if (ok) a.f[i * L.plane + L.at(tx + 1, ty)] = f[i];
         }
     } else if (idx - n_ring < n_fill) {
@@ -299,6 +302,37 @@ __global__ void k_aa_unwrap(double* __restrict__ f, Layout L, int do_x, int do_y
             f[south[k] * L.plane + L.at(t, L.ny - 1)] = f[south[k] * L.plane + L.at(t, -1)];
         }
     }
+}
+
+// x-slabs: the two wraps of the periodic case go ACROSS GPUs, as plain stores into the neighbour's memory (CUDA IPC peer
+// memory over NVLink) followed by the step-counter hand-shake of lbm_device.cuh.
+//   forward (after an E-step): my edge columns, all nine reversed slots, into the neighbours' ghost columns -- what
+//                              their O-step pulls across the face;
+//   reverse (after an O-step): what my cells pushed into MY ghost columns belongs to the neighbours' edge columns
+//                              (slots 1,5,8 eastwards, 3,6,7 westwards); their O-step touches none of those slots.
+__global__ void __launch_bounds__(256) k_aa_halo(const double* __restrict__ f, Layout L, int reverse, int rows_open, P2pArgs px) {
+    pdl_wait();
+    pdl_release();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = rows_open ? t - 1 : t;
+    const bool in = rows_open ? (y <= L.ny) : (y < L.ny);
+    if (in) {
+        if (!reverse) {
+#pragma unroll
+            for (int i = 0; i < Q; ++i) {
+                if (px.peer_dst_east) px.peer_dst_east[i * L.plane + L.at(0, y)] = f[i * L.plane + L.at(L.lnx, y)];
+                if (px.peer_dst_west) px.peer_dst_west[i * L.plane + L.at(L.lnx + 1, y)] = f[i * L.plane + L.at(1, y)];
+            }
+        } else {
+            const int east[3] = {1, 5, 8}, west[3] = {3, 6, 7};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (px.peer_dst_east) px.peer_dst_east[east[k] * L.plane + L.at(1, y)] = f[east[k] * L.plane + L.at(L.lnx + 1, y)];
+                if (px.peer_dst_west) px.peer_dst_west[west[k] * L.plane + L.at(L.lnx, y)] = f[west[k] * L.plane + L.at(0, y)];
+            }
+        }
+    }
+    p2p_block_end(px, gridDim.x);
 }
 
 // Ghost ring of the single buffer: reversed constants on non-periodic edges.
@@ -364,7 +398,7 @@ __device__ __forceinline__ void aa_current(const AaObserve& o, int x, int y, dou
             if (solid && i == 0) v = o.bc.w[0];  // its own rest population never left w
             if (solid && i > 0) {  // nobody filled the slots of a solid cell: rebuild what it would have pulled
                 const int nx_ = x - cxi(i), ny_ = y - cyi(i);
-                const bool out_x = !o.periodic_x && (nx_ < 0 || nx_ >= L.lnx);
+                const bool out_x = (nx_ < 0 && !o.open_w) || (nx_ >= L.lnx && !o.open_e);
                 const bool out_y = !o.periodic_y && (ny_ < 0 || ny_ >= L.ny);
                 if (out_x || out_y)
                     v = out_y ? o.bc.e[i] : 0.0;  // S/N ghost rows and corners: eq(1,u_in,0); W/E columns: 0 (F4)
@@ -550,6 +584,10 @@ cudaError_t launch_aa_unwrap(double* f, const Layout& L, int do_x, int do_y, cud
     if (do_x) e = launch_chain(k_aa_unwrap, dim3(cdiv(L.ny + 2, 256)), dim3(256), s, f, L, 1, 0, do_y);
     if (do_y && e == cudaSuccess) e = launch_chain(k_aa_unwrap, dim3(cdiv(L.lnx + 2, 256)), dim3(256), s, f, L, 0, 1, 0);
     return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+cudaError_t launch_aa_halo(const double* f, const Layout& L, int reverse, int rows_open, const P2pArgs& px, cudaStream_t s) {
+    return launch_chain(k_aa_halo, dim3(cdiv(L.ny + 2, 256)), dim3(256), s, f, L, reverse, rows_open, px);
 }
 
 cudaError_t launch_aa_ghosts(double* f, const Layout& L, const BcArgs& b, int west_zero, int east_zero, cudaStream_t s) {

@@ -89,7 +89,7 @@ struct lbm_solver {
     long long* d_custom_off = nullptr;  // lbm_upload_f_next: (offset, value) of the solid / ghost-row populations written
     double* d_custom_val = nullptr;
     int n_custom = 0;
-    bool custom_pending = false;  // ... to be installed right after the next iteration (see lbm_upload_f_next)
+    int custom_pending = 0;  // ... to be installed into the destination of each of the next two iterations (lbm_upload_f_next)
     bool custom_state = false;  // the caller wrote f_next (solid / ghost-row values may no longer be the constants the
                                 // temporally blocked passes build in): one-iteration kernels from then on
     int force_tree = 0;      // LBM_FORCES_TREE: fixed parallel reduction tree instead of the reference's serial order
@@ -240,8 +240,10 @@ AaObserve aa_observe(lbm_handle h) {
     o.ring_out = h->d_ring_out;
     o.periodic_x = h->periodic_x;
     o.periodic_y = h->periodic_y;
-    o.west_zero = h->periodic_x ? 0 : 1;
-    o.east_zero = h->periodic_x ? 0 : 1;
+    o.open_w = (h->periodic_x || h->west >= 0) ? 1 : 0;
+    o.open_e = (h->periodic_x || h->east >= 0) ? 1 : 0;
+    o.west_zero = (h->periodic_x || h->west >= 0) ? 0 : 1;
+    o.east_zero = (h->periodic_x || h->east >= 0) ? 0 : 1;
     o.shear_wave = (h->p.flags & LBM_FLAG_SHEAR_WAVE_INIT) ? 1 : 0;
     o.u0 = h->init_u;
     o.tau_inv = 1.0 / h->p.tau;
@@ -367,7 +369,8 @@ int build_geometry(lbm_handle h) {
                         // cell itself (through the reverse wrap if it crossed a periodic edge)
                         l.off = (long long)oppi(i) * L.plane + L.at(fx + 1, fy);
                         links_rev.push_back(l);
-                        const int sx = ((x % L.lnx) + L.lnx) % L.lnx;
+                        // (one periodic slab: through the reverse wrap; a slab interface: it sits in MY ghost column)
+                        const int sx = (h->periodic_x && h->world == 1) ? ((x % L.lnx) + L.lnx) % L.lnx : x;
                         l.off = (long long)i * L.plane + L.at(sx + 1, y);
                         links_nat.push_back(l);
                     }
@@ -382,7 +385,8 @@ int build_geometry(lbm_handle h) {
                 if (h->h_mask[L.at(x + 1, y)]) continue;
                 for (int i = 1; i < Q; ++i) {
                     const int nx_ = x - cxi(i), ny_ = y - cyi(i);
-                    const bool out_x = !h->periodic_x && (nx_ < 0 || nx_ >= L.lnx);
+                    // (a slab interface is an open edge: the neighbouring GPU's cells push across it)
+                    const bool out_x = (nx_ < 0 && !h->periodic_x && h->west < 0) || (nx_ >= L.lnx && !h->periodic_x && h->east < 0);
                     const bool out_y = !h->periodic_y && (ny_ < 0 || ny_ >= L.ny);
                     AaFill e;
                     e.off = (long long)i * L.plane + L.at(x + 1, y);
@@ -517,7 +521,9 @@ int setup_p2p(lbm_handle h) {
         CU(h, cudaGetDeviceProperties(&prop, h->device));
         std::memcpy(mine.uuid, prop.uuid.bytes, 16);
     }
-    ok = ok && cudaIpcGetMemHandle(&mine.f0, h->f[0]) == cudaSuccess && cudaIpcGetMemHandle(&mine.f1, h->f[1]) == cudaSuccess &&
+    // (the in-place variant has ONE population buffer: it stands for both)
+    ok = ok && cudaIpcGetMemHandle(&mine.f0, h->f[0]) == cudaSuccess &&
+         cudaIpcGetMemHandle(&mine.f1, h->f[1] ? h->f[1] : h->f[0]) == cudaSuccess &&
          cudaIpcGetMemHandle(&mine.flags, h->d_flags) == cudaSuccess;
     cudaGetLastError();
     Pack* d_io = nullptr;  // [0] mine, [1] from west, [2] from east
@@ -553,11 +559,13 @@ int setup_p2p(lbm_handle h) {
         if ((side == 0 ? h->west : h->east) < 0) continue;
         const Pack& p = got[1 + side];
         const cudaIpcMemHandle_t* hs[3] = {&p.f0, &p.f1, &p.flags};
-        for (int k = 0; k < 3 && ok; ++k)
+        for (int k = 0; k < 3 && ok; ++k) {
+            if (k == 1 && h->aa) continue;  // the same allocation as k == 0: open it once
             ok = cudaIpcOpenMemHandle(&h->ipc_opened[side][k], *hs[k], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+        }
         if (ok) {
             h->peer_f[side][0] = static_cast<double*>(h->ipc_opened[side][0]);
-            h->peer_f[side][1] = static_cast<double*>(h->ipc_opened[side][1]);
+            h->peer_f[side][1] = static_cast<double*>(h->aa ? h->ipc_opened[side][0] : h->ipc_opened[side][1]);
             h->peer_flags[side] = static_cast<int*>(h->ipc_opened[side][2]);
         }
     }
@@ -568,6 +576,8 @@ int setup_p2p(lbm_handle h) {
     CU(h, cudaMemcpyAsync(&agree, h->d_red, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     h->p2p = agree > 0.5;
+    if (h->aa && !h->p2p)
+        return fail(h, LBM_ERR_INVALID, "LBM_FLAG_AA over several slabs exchanges through CUDA IPC peer memory, which is unavailable here");
     return LBM_OK;
 }
 
@@ -620,6 +630,10 @@ const Link* aa_links(lbm_handle h) {
 int step_one_aa(lbm_handle h) {
     const Layout& L = h->L;
     const bool odd = h->aa_phase == 1;
+    if (odd && (h->west >= 0 || h->east >= 0)) {  // x-slabs: the neighbours' edge columns of the E-step must be in my ghost columns
+        int rc = join_halo(h);
+        if (rc) return rc;
+    }
     AaArgs a = aa_args(h, (!odd && !h->cur_is_next) ? 1 : 0);
     if (h->time_bulk && (h->iter % h->time_bulk) == 0) {
         cudaEvent_t e0, e1;
@@ -636,22 +650,47 @@ int step_one_aa(lbm_handle h) {
     } else {
         CU(h, launch_aa_bulk(odd, a, h->stream));
     }
+    const bool multi = h->west >= 0 || h->east >= 0;
+    const bool wrap_x1 = h->periodic_x && h->world == 1;  // the wrap stays inside this GPU
+    const int open_x = ((h->periodic_x || h->west >= 0) ? 1 : 0) | ((h->periodic_x || h->east >= 0) ? 2 : 0);
     if (!odd) {
         CU(h, launch_aa_fix_even(a, h->bc, h->d_ring, h->n_ring, h->d_solids, solids_to_reset(h, !a.first, true), h->stream));
         h->launches += 2;
-        if (h->periodic_x) { CU(h, launch_wrap(h->f[0], L, 1, 0, h->stream)); h->launches += 1; }
-        if (h->periodic_y) { CU(h, launch_wrap(h->f[0], L, 0, 1, h->stream)); h->launches += 1; }
+        if (wrap_x1) { CU(h, launch_wrap(h->f[0], L, 1, 0, h->stream)); h->launches += 1; }
+        if (multi) {
+            // forward halo: my edge columns into the neighbours' ghost columns; their O-step waits for it
+            h->edge_seq += 1;
+            CU(h, launch_aa_halo(h->f[0], L, 0, 0, p2p_args(h, 0, h->edge_seq), h->stream));
+            h->launches += 1;
+        }
+        if (h->periodic_y) {
+            if (multi) { int rc = join_halo(h); if (rc) return rc; }  // the corners copy the ghost columns
+            CU(h, launch_wrap(h->f[0], L, 0, 1, h->stream));
+            h->launches += 1;
+        }
     } else {
-        // Constant fill last: in a periodic direction the reverse wrap also carries what solid
-        // cells pushed across the edge, and the fill must overwrite that.
-        const bool wrap = h->periodic_x || h->periodic_y;
-        CU(h, launch_aa_fix_odd(a, h->bc, h->d_ring, h->n_ring, h->d_fills, wrap ? 0 : h->n_fill, h->d_ring_out,
-                                h->periodic_x ? 1 : 0, h->periodic_y ? 1 : 0, h->stream));
+        // Constant fill last: across an open edge the reverse wrap / halo also carries what solid cells
+        // pushed, and the fill must overwrite that.
+        const bool wrap = wrap_x1 || h->periodic_y || multi;
+        CU(h, launch_aa_fix_odd(a, h->bc, h->d_ring, h->n_ring, h->d_fills, wrap ? 0 : h->n_fill, h->d_ring_out, open_x,
+                                h->periodic_y ? 1 : 0, h->stream));
         h->launches += 2;
         if (wrap) {
-            CU(h, launch_aa_unwrap(h->f[0], L, h->periodic_x ? 1 : 0, h->periodic_y ? 1 : 0, h->stream));
+            if (wrap_x1 || h->periodic_y) {
+                CU(h, launch_aa_unwrap(h->f[0], L, wrap_x1 ? 1 : 0, h->periodic_y ? 1 : 0, h->stream));
+                h->launches += (wrap_x1 ? 1 : 0) + (h->periodic_y ? 1 : 0);
+            }
+            if (multi) {
+                // reverse halo: what my cells pushed across a face goes into the neighbour's edge column; mine arrives
+                // from the neighbours before the constants are filled in
+                h->edge_seq += 1;
+                CU(h, launch_aa_halo(h->f[0], L, 1, h->periodic_y ? 1 : 0, p2p_args(h, 0, h->edge_seq), h->stream));
+                h->launches += 1;
+                int rc = join_halo(h);
+                if (rc) return rc;
+            }
             CU(h, launch_aa_fix_odd(a, h->bc, h->d_ring, 0, h->d_fills, h->n_fill, h->d_ring_out, 0, 0, h->stream));
-            h->launches += (h->periodic_x ? 1 : 0) + (h->periodic_y ? 1 : 0) + (h->n_fill ? 1 : 0);
+            h->launches += (h->n_fill ? 1 : 0);
         }
     }
     h->aa_phase ^= 1;
@@ -956,10 +995,12 @@ int step_one(lbm_handle h) {
         h->pending.push_back({h->iter, slot});
     }
 
-    if (h->custom_pending) {
-        CU(h, launch_scatter(h->d_custom_off, h->d_custom_val, h->n_custom, h->f[0], h->f[1], h->stream));
+    if (h->custom_pending > 0) {
+        // into the buffer just written, never into the one just read: the observers of rho / u still rebuild the state
+        // the last collision saw from it, and that state was streamed from the OLD values
+        CU(h, launch_scatter(h->d_custom_off, h->d_custom_val, h->n_custom, dst, nullptr, h->stream));
         h->launches += 1;
-        h->custom_pending = false;
+        h->custom_pending -= 1;
     }
     h->cur ^= 1;
     h->prev_is_next = h->cur_is_next;
@@ -1040,6 +1081,7 @@ int ensure_stage(lbm_handle h) {
 int check_pending(lbm_handle h) {
     if (!h->cur_is_next) return LBM_OK;
     if (h->aa) {
+        { int rc_ = join_halo(h); if (rc_) return rc_; }
         CU(h, launch_aa_check(aa_observe(h), h->d_first_bad, h->iter - 1, h->stream));
         h->launches += 1;
         return LBM_OK;
@@ -1115,10 +1157,6 @@ int create_common(const lbm_params* p, int device, int rank, int world, const vo
     h->periodic_x = (p->flags & LBM_FLAG_PERIODIC_X) != 0;
     h->periodic_y = (p->flags & LBM_FLAG_PERIODIC_Y) != 0;
     h->aa = (p->flags & LBM_FLAG_AA) != 0;
-    if (h->aa && world > 1) {
-        delete h;
-        return fail(nullptr, LBM_ERR_INVALID, "LBM_FLAG_AA is a single-slab variant (the x-slab halo exchange is A-B only)");
-    }
     const int lnx = p->nx / world;
     h->L = Layout::make(lnx, p->ny, p->nx, rank * lnx);
     // include/LBMConfig.h:61-65
@@ -1360,7 +1398,7 @@ int lbm_initialise(lbm_handle h, double inlet_u) {
     h->lag = 1;
     h->macros_native_iter = -1;
     h->custom_state = false;
-    h->custom_pending = false;
+    h->custom_pending = 0;
     h->pending.clear();
     h->force_log.clear();
     if (h->p2p) return slab_barrier(h);  // every slab initialised before any neighbour pushes a halo into it
@@ -1629,7 +1667,8 @@ int lbm_upload_f_next(lbm_handle h, const double* aos) {
     // streaming has already consumed f_next and the next collision overwrites every FLUID cell, so fluid values are
     // dead; the values of solid cells and of the S/N ghost rows live on -- the NEXT iteration's streaming, and every
     // later one, pulls them.  The engine's fused step still owes the streaming of the iteration just finished (it
-    // must pull the OLD values), so the new ones are installed in both buffers right after the next step.
+    // must pull the OLD values), so the new ones go into the destination buffer of each of the next two steps (solid
+    // cells and ghost rows are never stored by the kernels: from then on both buffers keep them).
     const Layout& L = h->L;
     const size_t tnx = (size_t)L.lnx + 2;
     std::vector<long long> off;
@@ -1661,7 +1700,7 @@ int lbm_upload_f_next(lbm_handle h, const double* aos) {
         CU(h, cudaMemcpy(h->d_custom_off, off.data(), off.size() * sizeof(long long), cudaMemcpyHostToDevice));
         CU(h, cudaMemcpy(h->d_custom_val, val.data(), val.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
-    h->custom_pending = h->n_custom > 0;
+    h->custom_pending = h->n_custom > 0 ? 2 : 0;
     h->custom_state = true;
     return LBM_OK;
 }

@@ -152,6 +152,7 @@ struct AaObserve {
     int fresh;
     const double* ring_out;  // post-collision populations of the ring cells after an O-step
     int periodic_x, periodic_y;
+    int open_w, open_e;  // the edge is periodic or a slab interface: populations cross it
     int west_zero, east_zero;
     int shear_wave;
     double u0;
@@ -163,6 +164,9 @@ cudaError_t launch_aa_fix_even(const AaArgs& a, const BcArgs& b, const int2* rin
 cudaError_t launch_aa_fix_odd(const AaArgs& a, const BcArgs& b, const int2* ring, int n_ring, const AaFill* fills,
                               int n_fill, double* ring_out, int open_x, int open_y, cudaStream_t s);
 cudaError_t launch_aa_unwrap(double* f, const Layout& L, int do_x, int do_y, cudaStream_t s);
+// x-slabs: the forward wrap (after an E-step) / reverse wrap (after an O-step) into the neighbouring GPUs' memory,
+// then the hand-shake (publishes px.seq)
+cudaError_t launch_aa_halo(const double* f, const Layout& L, int reverse, int rows_open, const P2pArgs& px, cudaStream_t s);
 cudaError_t launch_aa_ghosts(double* f, const Layout& L, const BcArgs& b, int west_zero, int east_zero, cudaStream_t s);
 cudaError_t launch_aa_macros(const AaObserve& o, double* rho, double* ux, double* uy, cudaStream_t s);
 cudaError_t launch_aa_export(const AaObserve& o, int which, double* aos, int row0, int rows, cudaStream_t s);

@@ -21,7 +21,7 @@ def main():
 
     CASE = CASES[case_name]
 
-    params = util.case_to_params(CASE, flags=1 if case_name == "periodic" else 0)
+    params = util.case_to_params(CASE, flags=(1 if case_name == "periodic" else 0) | (16 if os.environ.get("LBM_TEST_AA") == "1" else 0))
     s, slab = lbm_b200.create_slab_solver(params, dist)
     s.initialise()
     if seed:

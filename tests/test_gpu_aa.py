@@ -115,10 +115,3 @@ def test_aa_equals_ab_in_the_extended_modes(flags, kw):
         assert np.array_equal(x[1], y[1]), ("f_current", k)
         assert x[2] == y[2], ("forces", k)
         assert np.abs(x[3][0] - y[3][0]).max() <= 1e-12 and np.abs(x[3][1] - y[3][1]).max() <= 1e-13
-
-
-def test_aa_is_refused_for_slabs():
-    import lbm_b200
-
-    with pytest.raises(lbm_b200.LbmError):
-        lbm_b200.Solver(lbm_b200.SimulationParams(nx=64, ny=32, flags=AA), rank=0, world=2, nccl_id=b"\0" * 128)

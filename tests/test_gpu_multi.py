@@ -154,3 +154,33 @@ def test_a_silent_neighbour_is_an_error_not_a_hang(tmp_path):
     assert int(res["halo_p2p"]) == 0 or (int(res["code"]) == -3 and float(res["seconds"]) < 60.0), (int(res["code"]), float(res["seconds"]))
     if int(res["halo_p2p"]):
         assert b"timed out" in bytes(res["message"])
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("seed,case_name,steps", [(5, "even", 37), (5, "even", 36), (0, "even", 21), (5, "odd", 37)])
+def test_in_place_aa_variant_over_slabs(tmp_path, world, seed, case_name, steps):
+    """LBM_FLAG_AA (ONE population buffer per GPU) over x-slabs: after every E-step the edge columns go to the
+    neighbours' ghost columns, after every O-step what was pushed across a face goes into the neighbours' edge
+    columns -- plain stores into peer memory plus the step-counter hand-shake.  Populations, f_current, forces rows
+    and the verdict bit-identical to the 1-rank oracle at both parities; rho / u to rounding (the single buffer
+    cannot keep them, tests/test_gpu_aa.py)."""
+    CASE = CASES[case_name]
+    if n_gpus() < world:
+        pytest.skip("needs %d GPUs" % world)
+    env = dict(os.environ, LBM_TEST_AA="1")
+    r = _torchrun(world, [str(tmp_path), str(steps), str(seed), case_name], env, 30200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    o = util.oracle_with_state(CASE, util.random_state(CASE, seed)) if seed else O.Oracle(CASE)
+    rows, bad = o.run(steps)
+    parts = [np.load(tmp_path / ("slab%d.npz" % k)) for k in range(world)]
+    for key, want in (("f_next", o.f_next[1:-1, 1:-1]), ("f_current", o.f_current[1:-1, 1:-1])):
+        got = np.concatenate([p[key] for p in parts], axis=1)
+        diff = (got != want).any(axis=2)
+        assert not diff.any(), "%s differs in %d cells, columns %s" % (key, int(diff.sum()), np.unique(np.nonzero(diff)[1])[:12])
+    for key, want, tol in (("rho", o.rho, 1e-14), ("ux", o.ux, 1e-14), ("uy", o.uy, 1e-14)):
+        got = np.concatenate([p[key] for p in parts], axis=1)
+        assert np.abs(got - want).max() <= tol, key
+    assert all(int(p["bad"]) == bad == -1 for p in parts)
+    assert all(int(p["halo_p2p"]) == 1 for p in parts)
+    total = sum(p["rows"][:, 1:3] for p in parts)
+    assert np.array_equal(parts[0]["rows"][:, 0], rows[:, 0]) and np.abs(total - rows[:, 1:3]).max() <= 1e-13
