@@ -89,31 +89,13 @@ void run_pass(int depth, int B, const TbArgs& a, int chunks) {
     }
 }
 
-}  // namespace
-
-extern "C" {
-
-// state:  global padded AoS [(gy*(nx+2)+gx)*9+i] (reference include/LBMGrid.h:105-107): a post-collision f_next
-//         (first_is_current = 0) or an f_current (first_is_current = 1: the first pass must have depth 1 and
-//         collides it in place).  Overwritten with f_next after the passes (interior cells; ghost ring untouched).
-// solid:  global padded mask [gy*(nx+2)+gx].
-// depths: the passes to run, n_pass of them.  world slabs of nx/world columns each exchange the wide halo the
-//         way the GPUs do (stores into the neighbour's ghost columns by the last stage).
-// flags:  1 periodic x, 2 periodic y.
-// Returns the smallest flagged timestep (bad_iter numbering starts at iter0 - 1) or INT_MAX.
-int tb_emulate(double* state, const unsigned char* solid, int nx, int ny, double tau, double u_in, int world, int flags,
-               const int* depths, int n_pass, int B, int xc, int edge_cols, int halo_w, int first_is_current, int iter0) {
-    const bool per_x = flags & 1, per_y = flags & 2;
+// One slab of the global state in the device Layout, both buffers, the mask with its deep flag (see tb_emulate for
+// the conventions: NaN wherever the kernel must never read).
+void init_slab(Slab& s, int r, int world, const double* state, const unsigned char* solid, int nx, int ny, const BcArgs& bc0,
+               bool per_x, bool per_y, int halo_w, int first_is_current) {
     const int lnx = nx / world;
-    std::vector<Slab> slabs(world);
-    BcArgs bc0{};
-    bc0.u_in = u_in;
-    equilibrium_init(1.0, 0.0, 0.0, bc0.w);
-    equilibrium_init(1.0, u_in, 0.0, bc0.e);
     auto g_at = [&](int gx, int gy) { return ((size_t)gy * (nx + 2) + gx) * Q; };
     const double nan = std::numeric_limits<double>::quiet_NaN();
-    for (int r = 0; r < world; ++r) {
-        Slab& s = slabs[r];
         s.L = Layout::make(lnx, ny, nx, r * lnx);
         for (int b = 0; b < 2; ++b) s.f[b].assign((size_t)s.L.plane * Q, nan);
         s.mask.assign((size_t)s.L.cells_padded(), 0);
@@ -163,7 +145,32 @@ int tb_emulate(double* state, const unsigned char* solid, int nx, int ny, double
             for (int y = 0; y < ny; ++y)
                 if (s.mask[s.L.at(gx, y)])
                     for (int i = 0; i < Q; ++i) s.f[1][i * s.L.plane + s.L.at(gx, y)] = bc0.w[i];
-    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// state:  global padded AoS [(gy*(nx+2)+gx)*9+i] (reference include/LBMGrid.h:105-107): a post-collision f_next
+//         (first_is_current = 0) or an f_current (first_is_current = 1: the first pass must have depth 1 and
+//         collides it in place).  Overwritten with f_next after the passes (interior cells; ghost ring untouched).
+// solid:  global padded mask [gy*(nx+2)+gx].
+// depths: the passes to run, n_pass of them.  world slabs of nx/world columns each exchange the wide halo the
+//         way the GPUs do (stores into the neighbour's ghost columns by the last stage).
+// flags:  1 periodic x, 2 periodic y.
+// Returns the smallest flagged timestep (bad_iter numbering starts at iter0 - 1) or INT_MAX.
+int tb_emulate(double* state, const unsigned char* solid, int nx, int ny, double tau, double u_in, int world, int flags,
+               const int* depths, int n_pass, int B, int xc, int edge_cols, int halo_w, int first_is_current, int iter0) {
+    const bool per_x = flags & 1, per_y = flags & 2;
+    const int lnx = nx / world;
+    std::vector<Slab> slabs(world);
+    BcArgs bc0{};
+    bc0.u_in = u_in;
+    equilibrium_init(1.0, 0.0, 0.0, bc0.w);
+    equilibrium_init(1.0, u_in, 0.0, bc0.e);
+    auto g_at = [&](int gx, int gy) { return ((size_t)gy * (nx + 2) + gx) * Q; };
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    for (int r = 0; r < world; ++r) init_slab(slabs[r], r, world, state, solid, nx, ny, bc0, per_x, per_y, halo_w, first_is_current);
     for (auto& s : slabs) wrap_ghosts(s, per_x && world == 1, per_y);
     int first_bad = 0x7fffffff;
     int iter = iter0;
@@ -232,6 +239,114 @@ int tb_emulate(double* state, const unsigned char* solid, int nx, int ny, double
                 for (int i = 0; i < Q; ++i) state[g_at(r * lnx + gx, y + 1) + i] = s.f[s.cur][i * s.L.plane + s.L.at(gx, y)];
     }
     return first_bad;
+}
+
+
+// ---- one slab per PROCESS (tests/test_slab_gloo.py, world_size 2 and 4 over gloo): the last stage's peer stores go into
+// out-boxes laid out like the neighbour's buffer; the test ships the halo region over gloo and puts it into the
+// receiver's ghost columns -- what NVLink does on the GPUs.
+struct SlabProc {
+    Slab s;
+    std::vector<double> out_w, out_e;
+    BcArgs bc0{};
+    int rank = 0, world = 1, halo_w = 2, lnx = 0, ny = 0;
+    double tau = 0.6;
+    int first_bad = 0x7fffffff;
+    bool first_is_current = false;
+    int passes = 0;
+};
+
+void* tbs_create(const double* state, const unsigned char* solid, int nx, int ny, double tau, double u_in, int rank, int world,
+                 int halo_w, int first_is_current) {
+    SlabProc* p = new SlabProc();
+    p->rank = rank; p->world = world; p->halo_w = halo_w; p->lnx = nx / world; p->ny = ny; p->tau = tau;
+    p->first_is_current = first_is_current != 0;
+    p->bc0.u_in = u_in;
+    equilibrium_init(1.0, 0.0, 0.0, p->bc0.w);
+    equilibrium_init(1.0, u_in, 0.0, p->bc0.e);
+    init_slab(p->s, rank, world, state, solid, nx, ny, p->bc0, false, false, halo_w, first_is_current);
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    p->out_w.assign((size_t)p->s.L.plane * Q, nan);
+    p->out_e.assign((size_t)p->s.L.plane * Q, nan);
+    return p;
+}
+
+void tbs_destroy(void* h) { delete static_cast<SlabProc*>(h); }
+
+// One pass of `depth` iterations starting with iteration `iter`; returns the smallest flagged timestep so far.
+int tbs_pass(void* h, int depth, int B, int xc, int edge_cols, int iter) {
+    SlabProc* p = static_cast<SlabProc*>(h);
+    Slab& s = p->s;
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    std::fill(p->out_w.begin(), p->out_w.end(), nan);
+    std::fill(p->out_e.begin(), p->out_e.end(), nan);
+    TbArgs a{};
+    a.src = s.f[s.cur].data();
+    a.dst = s.f[s.cur ^ 1].data();
+    a.L = s.L;
+    a.tau_inv = 1.0 / p->tau;
+    a.first_bad = &p->first_bad;
+    a.bad_iter = iter - 1;
+    a.bc = p->bc0;
+    a.bc.inlet = p->rank == 0 ? 1 : 0;
+    a.bc.outlet = p->rank == p->world - 1 ? 1 : 0;
+    a.bc.walls = 1;
+    a.mask = s.mask.data();
+    a.mask_lo = -Layout::XO;
+    a.mask_hi = p->lnx + 2 + Layout::XO;
+    a.west = p->rank > 0 ? TB_EDGE_HALO : TB_EDGE_CONST;
+    a.east = p->rank < p->world - 1 ? TB_EDGE_HALO : TB_EDGE_CONST;
+    a.pull = (p->passes == 0 && p->first_is_current) ? 0 : 1;
+    a.write = 1;
+    a.halo_w = p->halo_w;
+    a.edge_cols = edge_cols;
+    a.x_begin = edge_cols;
+    a.x_end = p->lnx - edge_cols;
+    a.xc = xc;
+    const int chunks = 2 + (a.x_end > a.x_begin ? (a.x_end - a.x_begin + xc - 1) / xc : 0);
+    a.px.peer_dst_west = p->rank > 0 ? p->out_w.data() : nullptr;
+    a.px.peer_dst_east = p->rank < p->world - 1 ? p->out_e.data() : nullptr;
+    tb_fill_offsets(a);
+    a.pf_dist = 1;
+    run_pass(depth, B, a, chunks);
+    if (!a.pull)
+        for (int gx = 1; gx <= p->lnx; ++gx)
+            for (int y = 0; y < p->ny; ++y)
+                if (s.mask[s.L.at(gx, y)])
+                    for (int i = 0; i < Q; ++i) s.f[s.cur][i * s.L.plane + s.L.at(gx, y)] = p->bc0.w[i];
+    s.cur ^= 1;
+    p->passes += 1;
+    return p->first_bad;
+}
+
+// What this slab's last pass stored for its neighbour: [halo_w][9][ny] (NaN where it stored nothing).
+void tbs_get_outbox(void* h, int east, double* buf) {
+    SlabProc* p = static_cast<SlabProc*>(h);
+    const Layout& L = p->s.L;
+    const std::vector<double>& box = east ? p->out_e : p->out_w;
+    for (int d = 0; d < p->halo_w; ++d)
+        for (int i = 0; i < Q; ++i)
+            for (int y = 0; y < p->ny; ++y)
+                buf[((size_t)d * Q + i) * p->ny + y] = box[i * L.plane + L.at(east ? -d : p->lnx + 1 + d, y)];
+}
+
+// ... lands in the receiver's newest buffer: from_east = it came from the east neighbour (its west out-box).
+void tbs_put_inbox(void* h, int from_east, const double* buf) {
+    SlabProc* p = static_cast<SlabProc*>(h);
+    Slab& s = p->s;
+    for (int d = 0; d < p->halo_w; ++d)
+        for (int i = 0; i < Q; ++i)
+            for (int y = 0; y < p->ny; ++y)
+                s.f[s.cur][i * s.L.plane + s.L.at(from_east ? p->lnx + 1 + d : -d, y)] = buf[((size_t)d * Q + i) * p->ny + y];
+}
+
+// interior populations of the newest buffer, [ny][lnx][9]
+void tbs_get_interior(void* h, double* out) {
+    SlabProc* p = static_cast<SlabProc*>(h);
+    const Slab& s = p->s;
+    for (int y = 0; y < p->ny; ++y)
+        for (int gx = 1; gx <= p->lnx; ++gx)
+            for (int i = 0; i < Q; ++i) out[((size_t)y * p->lnx + gx - 1) * Q + i] = s.f[s.cur][i * s.L.plane + s.L.at(gx, y)];
 }
 
 }  // extern "C"

@@ -42,7 +42,8 @@ def _built_once():
     (a no-op `make` otherwise).  nvcc cross-compiles without a GPU."""
     pkg = os.path.join(ROOT, "highperformancecomputing-latticeboltzmannmethod_b200")
     needed = [os.path.join(pkg, "liblbm_b200.so"), os.path.join(ROOT, "oracle", "liboracle.so"),
-              os.path.join(ROOT, "oracle", "prototypes", "libtb2.so"), os.path.join(ROOT, "examples", "lbm_solver")]
+              os.path.join(ROOT, "oracle", "prototypes", "libtb2.so"), os.path.join(ROOT, "oracle", "prototypes", "libtbemul.so"),
+              os.path.join(ROOT, "examples", "lbm_solver")]
     if all(os.path.exists(p) for p in needed):
         return  # shipped prebuilt (the GPU box gets the built files, not the object directory)
     import __graft_entry__ as g

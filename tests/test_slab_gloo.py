@@ -104,3 +104,93 @@ def test_slab_rules():
     assert (p.west, p.east, p.has_inlet) == (3, 1, False)
     with pytest.raises(ValueError):
         lbm_b200.Slab(0, 3, 64, 8)
+
+
+# ---- the temporally blocked passes over slabs, one slab per PROCESS, wide halo over gloo --------------------------
+def _tb_worker(rank, world, port, case_kw, depths, halo_w, out_dir):
+    """Each rank runs the sm_100a kernel's own thread program for its slab on the host (oracle/prototypes/tb_emul.cpp)
+    and ships what the last stage stored for its neighbours -- the wide halo the GPUs push over NVLink -- over gloo."""
+    import ctypes as C
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as O
+
+    case = O.Case(**case_kw)
+    o = O.Oracle(case)
+    rng = np.random.default_rng(21)  # (same seed on every rank: the global start state)
+    w = np.array([4 / 9] + [1 / 9] * 4 + [1 / 36] * 4)
+    init = o.f_current.copy()
+    f = w * (1.0 + 0.05 * rng.standard_normal((case.ny + 2, case.nx + 2, 9)))
+    for sl in ((0, slice(None)), (-1, slice(None)), (slice(None), 0), (slice(None), -1)):
+        f[sl] = init[sl]
+    o.f_current[...] = f
+    o.run(1)
+    state = np.ascontiguousarray(o.f_next.copy())
+    solid = np.zeros((case.ny + 2, case.nx + 2), dtype=np.uint8)
+    solid[1:-1, 1:-1] = o.solid
+    L = C.CDLL(os.path.join(ROOT, "oracle", "prototypes", "libtbemul.so"))
+    L.tbs_create.restype = C.c_void_p
+    L.tbs_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.tbs_pass.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    for name in ("tbs_get_outbox", "tbs_put_inbox"):
+        getattr(L, name).argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.tbs_get_interior.argtypes = [C.c_void_p, C.c_void_p]
+    L.tbs_destroy.argtypes = [C.c_void_p]
+    h = L.tbs_create(state.ctypes.data, solid.ctypes.data, case.nx, case.ny, case.tau, case.inlet_velocity, rank, world, halo_w, 0)
+    lnx, ny, it = case.nx // world, case.ny, 1
+    west, east = (rank - 1 if rank > 0 else -1), (rank + 1 if rank < world - 1 else -1)
+    sent = 0
+    for depth in depths:
+        bad = L.tbs_pass(h, depth, 16, 5, max(halo_w, 3), it)
+        assert bad == 0x7fffffff
+        it += depth
+        reqs, inbox = [], {}
+        for to_east, peer in ((1, east), (0, west)):
+            if peer < 0:
+                continue
+            box = np.empty((halo_w, 9, ny))
+            L.tbs_get_outbox(h, to_east, box.ctypes.data)
+            sent += int(np.isfinite(box).sum()) * 8
+            inbox[to_east] = torch.empty(halo_w, 9, ny, dtype=torch.float64)
+            reqs.append(dist.isend(torch.from_numpy(box), peer, tag=to_east))
+            reqs.append(dist.irecv(inbox[to_east], peer, tag=1 - to_east))
+        for r in reqs:
+            r.wait()
+        for side, buf in inbox.items():  # what arrived from the neighbour on that side
+            L.tbs_put_inbox(h, side, np.ascontiguousarray(buf.numpy()).ctypes.data)
+    out = np.empty((ny, lnx, 9))
+    L.tbs_get_interior(h, out.ctypes.data)
+    L.tbs_destroy(h)
+    np.savez(os.path.join(out_dir, "tb%d.npz" % rank), f_next=out, sent=sent, passes=len(depths))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,depths,halo_w", [(2, (2, 2, 1, 2), 2), (4, (2, 1, 2), 2), (2, (3, 2, 3), 3)])
+def test_temporally_blocked_slabs_with_the_wide_halo_over_gloo(tmp_path, world, depths, halo_w):
+    from oracle import oracle as O
+
+    case_kw = dict(nx=32 * world, ny=24, cylinder_x=1.0 / world if world > 1 else 0.5, cylinder_radius=0.2, output_frequency=5,
+                   inlet_velocity=0.04)
+    port = 29300 + (os.getpid() % 200) + 7 * world + halo_w
+    mp.spawn(_tb_worker, args=(world, port, case_kw, depths, halo_w, str(tmp_path)), nprocs=world, join=True)
+    case = O.Case(**case_kw)
+    o = O.Oracle(case)
+    rng = np.random.default_rng(21)
+    w = np.array([4 / 9] + [1 / 9] * 4 + [1 / 36] * 4)
+    init = o.f_current.copy()
+    f = w * (1.0 + 0.05 * rng.standard_normal((case.ny + 2, case.nx + 2, 9)))
+    for sl in ((0, slice(None)), (-1, slice(None)), (slice(None), 0), (slice(None), -1)):
+        f[sl] = init[sl]
+    o.f_current[...] = f
+    o.run(1 + sum(depths))
+    parts = [np.load(tmp_path / ("tb%d.npz" % r)) for r in range(world)]
+    got = np.concatenate([p["f_next"] for p in parts], axis=1)
+    assert np.array_equal(got, o.f_next[1:-1, 1:-1])
+    # the wire traffic of a pass: per face 3 population columns for the farthest halo column, 6 for the next,
+    # 9 beyond (lbm_tb.cuh tb_push) -- 9 columns per face at depth 2, 18 at depth 3
+    per_face = sum(3 if d == halo_w - 1 else (6 if d == halo_w - 2 else 9) for d in range(halo_w)) * case.ny * 8
+    assert int(parts[0]["sent"]) == per_face * len(depths)           # an end slab: one face
+    if world > 2:
+        assert int(parts[1]["sent"]) == 2 * per_face * len(depths)   # a middle slab: two faces
