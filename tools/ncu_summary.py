@@ -31,6 +31,11 @@ KEEP = [
     "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__waves_per_multiprocessor",
     "launch__occupancy_limit_registers", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
     "sm__inst_executed_pipe_fp64.sum", "smsp__inst_executed.sum", "lts__t_bytes.sum",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "launch__occupancy_limit_shared_mem", "smsp__warps_eligible.avg.per_cycle_active",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
     "l1tex__t_bytes_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_bytes_pipe_lsu_mem_global_op_st.sum",
     "smsp__cycles_active.avg", "sm__cycles_elapsed.max",
 ]
@@ -67,7 +72,7 @@ if os.path.exists(src) and suffix == "bulk":
         f.write("| kernel | launches | total ms | avg us | share | grid | block |\n|---|---:|---:|---:|---:|---|---|\n")
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write("| `%s` | %d | %.3f | %.1f | %.1f %% | %s | %s |\n" % (k, a[0], a[1] / 1e6, a[1] / a[0] / 1e3, 100 * a[1] / total, a[2], a[3]))
-        step = {k: a for k, a in agg.items() if k.startswith(("k_bulk", "k_fixup", "k_forces", "k_wrap"))}
+        step = {k: a for k, a in agg.items() if k.startswith(("k_tb", "k_bulk", "k_fixup", "k_forces", "k_wrap"))}
         st = sum(a[1] for a in step.values())
         if st:
             f.write("\nStep kernels only (what the timed region of bench.py launches):\n\n")
@@ -90,7 +95,7 @@ if os.path.exists(rep):
         for d in all_data:
             w.writerow([short(d[head.index("Kernel Name")])] + [d[c] for c in cols])
     # the traffic figure is that of the dominant (bulk collide-stream) kernel only
-    data = [d for d in all_data if re.search(r"k_bulk|k_aa_(odd|even)", d[head.index("Kernel Name")])]
+    data = [d for d in all_data if re.search(r"k_tb|k_bulk|k_aa_(odd|even)", d[head.index("Kernel Name")])]
 
     def col(name):
         c = head.index(name)
