@@ -21,6 +21,7 @@
 #include <cstring>
 #include <initializer_list>
 #include <string>
+#include <fcntl.h>
 #include <unistd.h>
 #include <vector>
 
@@ -1919,26 +1920,42 @@ int lbm_bootstrap_env(int* rank, int* world, int* local_rank, void* id128) {
     else
         std::snprintf(path, sizeof(path), "/tmp/lbm_b200_nccl_%ld_%s.id", (long)getppid(),
                       std::getenv("MASTER_PORT") ? std::getenv("MASTER_PORT") : "0");
+    // File format: 8 bytes magic, 8 bytes launch stamp, 128 bytes id.  The stamp is the launcher's start time where
+    // the launcher exports one (TORCHELASTIC_RUN_ID / SLURM_JOB_ID / the parent's pid as a last resort), so that a file
+    // left behind by an earlier launch with the same parent pid and port is never taken for this launch's.
+    unsigned long long stamp = 1469598103934665603ULL;
+    for (const char* name : {"TORCHELASTIC_RUN_ID", "SLURM_JOB_ID", "LBM_B200_LAUNCH_ID"})
+        if (const char* v = std::getenv(name))
+            for (const char* c = v; *c; ++c) stamp = (stamp ^ (unsigned char)*c) * 1099511628211ULL;
+    stamp ^= (unsigned long long)getppid() * 0x9E3779B97F4A7C15ULL;
+    const unsigned long long magic = 0x4c424d4e43434c49ULL;
     if (rr == 0) {
         int rc = lbm_nccl_unique_id(id128);
         if (rc) return rc;
-        std::string tmp = std::string(path) + ".tmp";
-        FILE* f = std::fopen(tmp.c_str(), "wb");
-        if (!f || std::fwrite(id128, 1, 128, f) != 128) {
-            if (f) std::fclose(f);
+        // created exclusively, owner-only, under a private temporary name (a pre-created file or symlink at that name
+        // makes the open fail instead of being followed), then renamed into place
+        std::string tmp = std::string(path) + "." + std::to_string((long)getpid()) + ".tmp";
+        unlink(tmp.c_str());
+        unlink(path);  // a stale file of an earlier launch
+        const int fd = open(tmp.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_NOFOLLOW, 0600);
+        bool ok = fd >= 0;
+        ok = ok && write(fd, &magic, 8) == 8 && write(fd, &stamp, 8) == 8 && write(fd, id128, 128) == 128;
+        if (fd >= 0) close(fd);
+        if (!ok) {
+            unlink(tmp.c_str());
             return fail(nullptr, LBM_ERR_IO, std::string("cannot write ") + tmp);
         }
-        std::fclose(f);
         if (std::rename(tmp.c_str(), path) != 0) return fail(nullptr, LBM_ERR_IO, std::string("cannot rename to ") + path);
         g_id_file = path;  // removed once every rank has joined the communicator (create_common)
         return LBM_OK;
     }
     for (int tries = 0; tries < 6000; ++tries) {  // up to 60 s
-        FILE* f = std::fopen(path, "rb");
-        if (f) {
-            const size_t n = std::fread(id128, 1, 128, f);
-            std::fclose(f);
-            if (n == 128) return LBM_OK;
+        const int fd = open(path, O_RDONLY | O_NOFOLLOW);
+        if (fd >= 0) {
+            unsigned long long head[2] = {0, 0};
+            const bool ok = read(fd, head, 16) == 16 && head[0] == magic && head[1] == stamp && read(fd, id128, 128) == 128;
+            close(fd);
+            if (ok) return LBM_OK;
         }
         usleep(10000);
     }

@@ -16,14 +16,14 @@ namespace {
 // chunks are still being worked on.
 // Occupancy: the ring of a depth-2 pass (72 B per thread and slot) lets 768 threads share an SM's shared memory; the
 // launch bound asks for exactly that, i.e. at most 85 registers per thread.
-template <int T, int B, bool FORCED>
+template <int T, int B, bool FORCED, bool UNROLL2 = true>
 __global__ void __launch_bounds__(B, (T == 3 ? 256 : 768) / B) k_tb(const __grid_constant__ TbArgs a, int p2p) {
     extern __shared__ double ring[];
     pdl_wait();
     pdl_release();
     const bool edge_block = p2p && blockIdx.y < 2;
     if (edge_block) p2p_block_begin(a.px);
-    tb_thread<T, B, FORCED>(a, ring, threadIdx.x, blockIdx.x, blockIdx.y);
+    tb_thread<T, B, FORCED, UNROLL2>(a, ring, threadIdx.x, blockIdx.x, blockIdx.y);
     if (edge_block) p2p_block_end(a.px, gridDim.x * 2);
 }
 
@@ -73,10 +73,10 @@ int env_int(const char* name, int dflt) {
     return v ? std::atoi(v) : dflt;
 }
 
-template <int T, int B, bool FORCED>
+template <int T, int B, bool FORCED, bool UNROLL2 = true>
 cudaError_t launch_one(TbArgs a, bool p2p, cudaStream_t s) {
     using S = TbShape<T, B>;
-    auto kern = k_tb<T, B, FORCED>;
+    auto kern = k_tb<T, B, FORCED, UNROLL2>;
     const size_t smem = (size_t)S::RING_DOUBLES * sizeof(double);
     static int slots = 0;  // resident blocks on the whole device, per instantiation
     if (!slots) {

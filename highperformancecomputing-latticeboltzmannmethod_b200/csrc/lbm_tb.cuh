@@ -87,6 +87,16 @@ LBM_HD P tb_opaque(P p) {
 #endif
     return p;
 }
+// The same for a 32-bit value.  Used for the thread / block indices: re-read from the special registers inside the
+// march loop (S2R, which the compiler prefers to spending a register) they sit on a scoreboard shared with the
+// prefetch loads just issued, and their first use then waits for a whole trip to memory.
+// (A warp shuffle of the value with itself: the one thing neither compiler stage re-derives from %tid / %ctaid.)
+LBM_HD int tb_opaque_int(int v) {
+#if defined(__CUDA_ARCH__)
+    v = __shfl_sync(0xffffffffu, v, threadIdx.x & 31);
+#endif
+    return v;
+}
 
 // ---- host / device glue (the host side exists for the thread-for-thread emulation only) ----------
 #if defined(__CUDA_ARCH__)
@@ -431,9 +441,10 @@ LBM_HD void tb_step(const TbArgs& a, const TbRow<T, B>& r, double* ring, int s, 
 
 // One thread of one block: `tid` in [0, B), rows of strip `strip`, columns of chunk `chunk`.
 // `ring` is the block's shared memory (TbShape::RING_DOUBLES doubles).
-template <int T, int B, bool FORCED>
-LBM_HD void tb_thread(const TbArgs& a, double* ring, int tid, int strip, int chunk) {
+template <int T, int B, bool FORCED, bool UNROLL2 = true>
+LBM_HD void tb_thread(const TbArgs& a, double* ring, int tid_, int strip_, int chunk_) {
     using S = TbShape<T, B>;
+    const int tid = tb_opaque_int(tid_), strip = tb_opaque_int(strip_), chunk = tb_opaque_int(chunk_);
     const int ny = a.L.ny, lnx = a.L.lnx;
     TbRow<T, B> r;
     tb_chunk(a, chunk, r.x0, r.x1, r.edge);
@@ -502,21 +513,19 @@ LBM_HD void tb_thread(const TbArgs& a, double* ring, int tid, int strip, int chu
     // the columns s-(T-1) .. s+1 a step touches may hold obstacle cells iff they meet [mask_lo - 1, mask_hi - 1)
     const int m0 = a.mask_lo - 2, m1 = a.mask_hi - 1 + (T - 1);  // steps s in [m0, m1) are masked
     while (s <= s_last) {
-        if (s >= p0 && s < p1) {
-            // a stretch of lean steps, unrolled by two so that the two cells keep their roles (no register copies)
-            if (!a_is_cur) {
-                tb_step<T, B, FORCED, true>(a, r, ring, s, true, s >= m0 && s < m1, cb, ca, bad);
-                a_is_cur = true;
-                ++s;
-            }
-            for (; s + 1 < p1; s += 2) {
-                tb_step<T, B, FORCED, true>(a, r, ring, s, true, s >= m0 && s < m1, ca, cb, bad);
-                tb_step<T, B, FORCED, true>(a, r, ring, s + 1, true, s + 1 >= m0 && s + 1 < m1, cb, ca, bad);
-            }
-            if (s < p1) {
-                tb_step<T, B, FORCED, true>(a, r, ring, s, true, s >= m0 && s < m1, ca, cb, bad);
-                a_is_cur = false;
-                ++s;
+        if (a_is_cur && s >= p0 && s + (UNROLL2 ? 1 : 0) < p1) {
+            if (UNROLL2) {
+                // a stretch of lean steps, unrolled by two so that the two cells keep their roles (no register copies)
+                for (; s + 1 < p1; s += 2) {
+                    tb_step<T, B, FORCED, true>(a, r, ring, s, true, s >= m0 && s < m1, ca, cb, bad);
+                    tb_step<T, B, FORCED, true>(a, r, ring, s + 1, true, s + 1 >= m0 && s + 1 < m1, cb, ca, bad);
+                }
+            } else {
+                // ... or one copy of the step and a register-to-register copy of the prefetched cell (half the code)
+                for (; s < p1; ++s) {
+                    tb_step<T, B, FORCED, true>(a, r, ring, s, true, s >= m0 && s < m1, ca, cb, bad);
+                    ca = cb;
+                }
             }
             continue;
         }

@@ -66,7 +66,7 @@ if os.path.exists(src) and suffix == "bulk":
         a[1] += ns
     total = sum(a[1] for a in agg.values())
     with open(os.path.join(P, tag + "_launches_summary.md"), "w") as f:
-        f.write("# %s: every kernel launch of `python bench.py --steps 20 --warmup 3 --no-cpu-baseline` (workload %s)\n\n" % (tag, workload))
+        f.write("# %s: every kernel launch of `python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-parity` (workload %s)\n\n" % (tag, workload))
         f.write("ncu `--metrics gpu__time_duration.sum --clock-control none`; per-launch times are cold-cache and\n"
                 "serialised, so compare SHARES.  %d launches, %.3f ms of kernel time in total.\n\n" % (len(rows), total / 1e6))
         f.write("| kernel | launches | total ms | avg us | share | grid | block |\n|---|---:|---:|---:|---:|---|---|\n")
