@@ -10,20 +10,24 @@ namespace lbm {
 
 namespace {
 
+#ifndef TB_SKEW_THREADS
+#define TB_SKEW_THREADS 512
+#endif
+
 // One block = B threads on B consecutive rows, marching through its chunk of columns.  In a multi-slab
 // job the blocks of chunks 0 and 1 (the slab-edge columns) run the peer-memory hand-shake around their
 // march: they are the first blocks of the grid, so the neighbours get their halo while the interior
 // chunks are still being worked on.
 // Occupancy: the ring of a depth-2 pass (72 B per thread and slot) lets 768 threads share an SM's shared memory; the
 // launch bound asks for exactly that, i.e. at most 85 registers per thread.
-template <int T, int B, bool FORCED, bool UNROLL2 = true>
-__global__ void __launch_bounds__(B, (T == 3 ? 256 : 768) / B) k_tb(const __grid_constant__ TbArgs a, int p2p) {
+template <int T, int B, bool FORCED, bool SKEW = true>
+__global__ void __launch_bounds__(B, (T == 3 ? 384 : (SKEW && T == 2 ? TB_SKEW_THREADS : 768)) / B) k_tb(const __grid_constant__ TbArgs a, int p2p) {
     extern __shared__ double ring[];
     pdl_wait();
     pdl_release();
     const bool edge_block = p2p && blockIdx.y < 2;
     if (edge_block) p2p_block_begin(a.px);
-    tb_thread<T, B, FORCED, UNROLL2>(a, ring, threadIdx.x, blockIdx.x, blockIdx.y);
+    tb_thread<T, B, FORCED, SKEW>(a, ring, threadIdx.x, blockIdx.x, blockIdx.y);
     if (edge_block) p2p_block_end(a.px, gridDim.x * 2);
 }
 
@@ -73,10 +77,10 @@ int env_int(const char* name, int dflt) {
     return v ? std::atoi(v) : dflt;
 }
 
-template <int T, int B, bool FORCED, bool UNROLL2 = true>
+template <int T, int B, bool FORCED, bool SKEW = true>
 cudaError_t launch_one(TbArgs a, bool p2p, cudaStream_t s) {
     using S = TbShape<T, B>;
-    auto kern = k_tb<T, B, FORCED, UNROLL2>;
+    auto kern = k_tb<T, B, FORCED, SKEW>;
     const size_t smem = (size_t)S::RING_DOUBLES * sizeof(double);
     static int slots = 0;  // resident blocks on the whole device, per instantiation
     if (!slots) {
@@ -136,6 +140,8 @@ cudaError_t launch_one(TbArgs a, bool p2p, cudaStream_t s) {
 template <int T, int B>
 cudaError_t launch_forced(const TbArgs& a, bool p2p, cudaStream_t s) {
     const bool forced = (a.Fx != 0.0 || a.Fy != 0.0);
+    static const bool skew = env_int("LBM_B200_TB_SKEW", 1) != 0;
+    if (T == 2 && !forced && !skew) return launch_one<T, B, false, false>(a, p2p, s);  // (the one-column-lag march, for A/B runs)
     return forced ? launch_one<T, B, true>(a, p2p, s) : launch_one<T, B, false>(a, p2p, s);
 }
 
@@ -156,7 +162,7 @@ cudaError_t launch_tb(int depth, TbArgs a, bool p2p, cudaStream_t s) {
     switch (depth) {
         case 1: return small ? launch_forced<1, 128>(a, p2p, s) : launch_forced<1, 256>(a, p2p, s);
         case 2: return small ? launch_forced<2, 128>(a, p2p, s) : launch_forced<2, 256>(a, p2p, s);
-        case 3: return launch_forced<3, 256>(a, p2p, s);
+        case 3: return small ? launch_forced<3, 128>(a, p2p, s) : launch_forced<3, 256>(a, p2p, s);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -167,16 +173,16 @@ cudaError_t launch_tb(int depth, TbArgs a, bool p2p, cudaStream_t s) {
 bool tb_worthwhile(const Layout& L) {
     const int b = block_threads();
     const long long blocks = (long long)cdiv(L.ny, b - 4) * cdiv(L.lnx, 64);
-    return blocks >= 2LL * 148 * (768 / b);
+    return blocks >= 2LL * 148 * (TB_SKEW_THREADS / b);
 }
 
 int tb_rows_per_block(int depth) {
-    const int b = depth == 3 ? 256 : block_threads();
+    const int b = block_threads();
     return depth == 1 ? b : b - 4;
 }
 
 size_t tb_shared_bytes(int depth) {
-    const int b = depth == 3 ? 256 : block_threads();
+    const int b = block_threads();
     return (size_t)(depth - 1) * TB_SLOTS * Q * b * sizeof(double);
 }
 

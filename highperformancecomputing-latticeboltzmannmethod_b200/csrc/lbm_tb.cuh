@@ -439,9 +439,29 @@ LBM_HD void tb_step(const TbArgs& a, const TbRow<T, B>& r, double* ring, int s, 
     }
 }
 
+// The SKEWED march step (the default): stage k works on column s - 2(k-1), TWO columns behind stage k-1 instead of
+// one.  Everything stage k reads was then written in EARLIER steps, so the T stages of a step are independent of one
+// another: the loads of stage 1's column are issued first, the later stages (whose inputs are already in shared
+// memory) compute while those loads fly, stage 1 finishes last, and ONE barrier ends the step.  No second cell of
+// prefetched registers, no loop unrolled by two, and the instruction streams of the stages can overlap.
+template <int T, int B, bool FORCED, bool PLAIN>
+LBM_HD void tb_step_skew(const TbArgs& a, const TbRow<T, B>& r, double* ring, int s, bool masked, bool bad[T]) {
+    if (r.tid == 0 && r.pf_bytes > 0 && s + a.pf_dist <= r.pf_last) tb_prefetch_l2<T, B>(a, r.pf_seg, r.pf_bytes, s + a.pf_dist);
+    TbCell first;
+    tb_issue<T, B, PLAIN>(a, r, s, masked, first);
+#pragma unroll
+    for (int k = T; k >= 2; --k) {
+        TbCell cell;
+        tb_from_ring<T, B, PLAIN>(a, r, ring, k, s - 2 * (k - 1), masked, cell);
+        bad[k - 1] |= tb_finish<T, B, FORCED, PLAIN>(a, r, ring, k, s - 2 * (k - 1), cell);
+    }
+    bad[0] |= tb_finish<T, B, FORCED, PLAIN>(a, r, ring, 1, s, first);
+    if (T > 1) TB_SYNC();
+}
+
 // One thread of one block: `tid` in [0, B), rows of strip `strip`, columns of chunk `chunk`.
 // `ring` is the block's shared memory (TbShape::RING_DOUBLES doubles).
-template <int T, int B, bool FORCED, bool UNROLL2 = true>
+template <int T, int B, bool FORCED, bool SKEW = true>
 LBM_HD void tb_thread(const TbArgs& a, double* ring, int tid_, int strip_, int chunk_) {
     using S = TbShape<T, B>;
     const int tid = tb_opaque_int(tid_), strip = tb_opaque_int(strip_), chunk = tb_opaque_int(chunk_);
@@ -495,11 +515,29 @@ LBM_HD void tb_thread(const TbArgs& a, double* ring, int tid_, int strip_, int c
     for (int k = 0; k < T; ++k) bad[k] = false;
 
     // ---- the march ---------------------------------------------------------------------------------
-    // Steps whose T columns s, s-1, ..., s-(T-1) are all plain interior columns (not a ghost column, not the inlet
-    // or outlet column) with every stage inside its range take the lean path; [p0, p1) also keeps column s+1 plain.
-    const int s_first = r.x0 - (T - 1), s_last = r.x1 + (T - 2);
     const int c_lo = (a.west == TB_EDGE_CONST && a.bc.inlet) ? 1 : 0;           // first plain column
     const int c_hi = (a.east == TB_EDGE_CONST && a.bc.outlet) ? lnx - 1 : lnx;  // one past the last plain column
+    if (SKEW) {
+        // Stage k on column s - 2(k-1).  Steps whose T columns are all plain interior columns (not a ghost column, not
+        // the inlet or outlet column) with every stage inside its range take the lean path.
+        const int s_first = r.x0 - (T - 1), s_last = r.x1 - 1 + 2 * (T - 1);
+        int p0 = (r.x0 > c_lo ? r.x0 : c_lo) + 2 * (T - 1);
+        int p1 = (r.x1 + (T - 2) < c_hi - 1 ? r.x1 + (T - 2) : c_hi - 1) + 1;  // lean steps: [p0, p1)
+        if (r.edge) p1 = p0;  // the few slab-edge columns also feed the neighbour: general path
+        r.pf_last = r.x1 + (T - 2) < lnx ? r.x1 + (T - 2) : lnx;  // the last column stage 1 loads
+        // the columns s-2(T-1) .. s a step touches may hold obstacle cells iff they meet [mask_lo - 1, mask_hi - 1)
+        const int m0 = a.mask_lo - 1, m1 = a.mask_hi - 1 + 2 * (T - 1);  // steps s in [m0, m1) are masked
+        for (int s = s_first; s <= s_last; ++s) {
+            if (s >= p0 && s < p1)
+                tb_step_skew<T, B, FORCED, true>(a, r, ring, s, s >= m0 && s < m1, bad);
+            else
+                tb_step_skew<T, B, FORCED, false>(a, r, ring, s, true, bad);
+        }
+    } else {
+    // Stage k on column s - (k-1), stage 1's loads issued one step ahead into a second cell of registers.
+    // Steps whose T columns s, s-1, ..., s-(T-1) are all plain interior columns with every stage inside its range
+    // take the lean path; [p0, p1) also keeps column s+1 plain.
+    const int s_first = r.x0 - (T - 1), s_last = r.x1 + (T - 2);
     int p0 = r.x0 + (T - 1), p1 = s_last;  // every stage active for s in [x0+T-1, s_last]; s+1 <= s_last
     if (p0 < c_lo + (T - 1)) p0 = c_lo + (T - 1);
     if (p1 > c_hi - 1) p1 = c_hi - 1;
@@ -513,19 +551,11 @@ LBM_HD void tb_thread(const TbArgs& a, double* ring, int tid_, int strip_, int c
     // the columns s-(T-1) .. s+1 a step touches may hold obstacle cells iff they meet [mask_lo - 1, mask_hi - 1)
     const int m0 = a.mask_lo - 2, m1 = a.mask_hi - 1 + (T - 1);  // steps s in [m0, m1) are masked
     while (s <= s_last) {
-        if (a_is_cur && s >= p0 && s + (UNROLL2 ? 1 : 0) < p1) {
-            if (UNROLL2) {
-                // a stretch of lean steps, unrolled by two so that the two cells keep their roles (no register copies)
-                for (; s + 1 < p1; s += 2) {
-                    tb_step<T, B, FORCED, true>(a, r, ring, s, true, s >= m0 && s < m1, ca, cb, bad);
-                    tb_step<T, B, FORCED, true>(a, r, ring, s + 1, true, s + 1 >= m0 && s + 1 < m1, cb, ca, bad);
-                }
-            } else {
-                // ... or one copy of the step and a register-to-register copy of the prefetched cell (half the code)
-                for (; s < p1; ++s) {
-                    tb_step<T, B, FORCED, true>(a, r, ring, s, true, s >= m0 && s < m1, ca, cb, bad);
-                    ca = cb;
-                }
+        if (a_is_cur && s >= p0 && s + 1 < p1) {
+            // a stretch of lean steps, unrolled by two so that the two cells keep their roles (no register copies)
+            for (; s + 1 < p1; s += 2) {
+                tb_step<T, B, FORCED, true>(a, r, ring, s, true, s >= m0 && s < m1, ca, cb, bad);
+                tb_step<T, B, FORCED, true>(a, r, ring, s + 1, true, s + 1 >= m0 && s + 1 < m1, cb, ca, bad);
             }
             continue;
         }
@@ -533,6 +563,7 @@ LBM_HD void tb_thread(const TbArgs& a, double* ring, int tid_, int strip_, int c
         else tb_step<T, B, FORCED, false>(a, r, ring, s, s < s_last, true, cb, ca, bad);
         a_is_cur = !a_is_cur;
         ++s;
+    }
     }
 #pragma unroll
     for (int k = 0; k < T; ++k)

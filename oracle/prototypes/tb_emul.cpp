@@ -32,6 +32,8 @@ using namespace lbm;
 
 namespace {
 
+bool g_skew = true;  // which march (lbm_tb.cuh) the emulation runs; tb_set_skew
+
 struct Slab {
     Layout L;
     std::vector<double> f[2];
@@ -71,7 +73,8 @@ void run_blocks(const TbArgs& a, int chunks) {
             for (int tid = 0; tid < B; ++tid)
                 th.emplace_back([&, tid] {
                     g_barrier = &bar;
-                    tb_thread<T, B, false>(a, ring.data(), tid, strip, chunk);
+                    if (g_skew) tb_thread<T, B, false, true>(a, ring.data(), tid, strip, chunk);
+                    else tb_thread<T, B, false, false>(a, ring.data(), tid, strip, chunk);
                 });
             for (auto& t : th) t.join();
         }
@@ -150,6 +153,8 @@ void init_slab(Slab& s, int r, int world, const double* state, const unsigned ch
 }  // namespace
 
 extern "C" {
+
+void tb_set_skew(int on) { g_skew = on != 0; }
 
 // state:  global padded AoS [(gy*(nx+2)+gx)*9+i] (reference include/LBMGrid.h:105-107): a post-collision f_next
 //         (first_is_current = 0) or an f_current (first_is_current = 1: the first pass must have depth 1 and
