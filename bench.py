@@ -489,6 +489,12 @@ def main():
     sampler.start()
     windows = []
 
+    # Untimed: one output period first, so that every kernel of the path (the depth-1 pass of an output step, the
+    # force reduction, the macro emission) has been loaded and every lazily allocated buffer exists before anything is
+    # timed (CUDA loads kernels lazily; on a fresh box the first output step costs tens of milliseconds).
+    if p.output_frequency > 0:
+        s.run(p.output_frequency + 2)
+        s.max_velocity()
     # warm-up, then K timed steps bracketed by barrier + synchronize on both sides
     s.step(args.warmup)
     s.sync()

@@ -1386,6 +1386,10 @@ int lbm_initialise(lbm_handle h, double inlet_u) {
         h->launches += 1;
         h->aa_phase = 0;
     }
+    if (!h->aa && h->variant == BULK_TB) {  // (not in the middle of a run: cudaMalloc synchronises the device)
+        int rc = ensure_native_macros(h);
+        if (rc) return rc;
+    }
     const int big = INT_MAX;
     CU(h, cudaMemcpyAsync(h->d_first_bad, &big, sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));

@@ -18,10 +18,8 @@ namespace {
 // job the blocks of chunks 0 and 1 (the slab-edge columns) run the peer-memory hand-shake around their
 // march: they are the first blocks of the grid, so the neighbours get their halo while the interior
 // chunks are still being worked on.
-// Occupancy: the ring of a depth-2 pass (72 B per thread and slot) lets 768 threads share an SM's shared memory; the
-// launch bound asks for exactly that, i.e. at most 85 registers per thread.
-template <int T, int B, bool FORCED, bool SKEW = true>
-__global__ void __launch_bounds__(B, (T == 3 ? 384 : (SKEW && T == 2 ? TB_SKEW_THREADS : 768)) / B) k_tb(const __grid_constant__ TbArgs a, int p2p) {
+template <int T, int B, bool FORCED, bool SKEW>
+__device__ __forceinline__ void tb_kernel_body(const TbArgs& a, int p2p) {
     extern __shared__ double ring[];
     pdl_wait();
     pdl_release();
@@ -29,6 +27,16 @@ __global__ void __launch_bounds__(B, (T == 3 ? 384 : (SKEW && T == 2 ? TB_SKEW_T
     if (edge_block) p2p_block_begin(a.px);
     tb_thread<T, B, FORCED, SKEW>(a, ring, threadIdx.x, blockIdx.x, blockIdx.y);
     if (edge_block) p2p_block_end(a.px, gridDim.x * 2);
+}
+
+// Occupancy.  The skewed depth-2 march keeps two cells in registers (stage 1's loads in flight, the later stage being
+// computed): 128 registers, 512 threads = 16 warps per SM -- measured: ANY spill costs more than the warps it buys (96
+// registers / 20 warps: 42 800 MLUPS, 112 / 18: 53 300, 128 / 16: 65 800; the L1 left beside 148 KB of rings is
+// tiny).  The one-column-lag march fits 80 registers (768 threads); depth 3: 384 threads.
+template <int T, int B, bool FORCED, bool SKEW = true>
+__global__ void __launch_bounds__(B, (T == 3 ? 384 : ((SKEW && T == 2) || T == 1 ? TB_SKEW_THREADS : 768)) / B)
+    k_tb(const __grid_constant__ TbArgs a, int p2p) {
+    tb_kernel_body<T, B, FORCED, SKEW>(a, p2p);
 }
 
 // native [x*ny + y] -> interior row-major [y*lnx + x], 32 x 32 tiles through shared memory, with the
