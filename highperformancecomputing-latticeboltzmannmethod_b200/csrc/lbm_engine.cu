@@ -1425,10 +1425,10 @@ int lbm_step(lbm_handle h, int n_steps) {
     }
     for (int k = 0; k < n_steps;) {
         const int d = next_depth(h, n_steps - k);
-        const int last = h->iter + d - 1, of = h->p.output_frequency;
-        // Solver::run looks at rho / u after every output step (max_velocity, VTK), lbm_run's caller after the
-        // call: those passes emit the moments of their last collision (24 B per cell, once per output period)
-        const bool emit = (of > 0 && last > 0 && last % of == 0) || (h->emit_last && k + d == n_steps);
+        // The caller of lbm_run looks at rho / u after the call (Solver::run: max_velocity and VTK after every output
+        // step, and its chunks END on output steps): the last pass of such a call emits the moments of its last
+        // collision (24 B per cell).  Anywhere else an observer re-runs the pass store-less (ensure_macros).
+        const bool emit = h->emit_last && k + d == n_steps;
         int rc = step_tb(h, d, emit);
         if (rc) return rc;
         k += d;
