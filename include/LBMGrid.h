@@ -8,8 +8,10 @@
 //     index conventions (ghost-inclusive coordinates for populations, interior ones otherwise);
 //   * MPI_Cart_create + 2-D decomposition (:347-392) became contiguous x-slabs, one process per
 //     GPU, ranks discovered by lbm_bootstrap_env; mpi_rank()/mpi_size() report slab and count;
-//   * exchange_ghost_cells() is fused into the step (NCCL send/recv on a communication stream)
-//     and is a no-op here.
+//   * exchange_ghost_cells() is fused into the step kernels (stores into the neighbouring GPU's memory; NCCL
+//     send/recv where peer access is unavailable) and is a no-op here;
+//   * the constructor's banner names the slab partition instead of the reference's MPI grid (same fields, different
+//     first line).
 // Errors surface as std::runtime_error carrying lbm_last_error(), which src/main.cpp:29 catches.
 #pragma once
 

@@ -161,6 +161,11 @@ int lbm_gather_macros(lbm_handle h, double* rho, double* ux, double* uy);
 
 /* ---- observable state: Grid accessors (include/LBMGrid.h:115-129,145) ---- */
 enum { LBM_F_CURRENT = 0, LBM_F_NEXT = 1 };
+/* The padded AoS image of this slab.  Interior cells and the ghost ring of a single-slab handle equal the reference's
+ * arrays bit for bit.  In a multi-slab job the ghost columns of f_next at a slab INTERFACE hold only the populations
+ * the neighbouring GPU stores there (the ones this slab pulls across the face: 6 of 9 in the nearest column with the
+ * temporally blocked passes, 3 of 9 with the one-iteration kernels); the reference's exchange copies all nine
+ * (LBMGrid.h:395-491), none of the other six is ever read by an iteration. */
 int lbm_download_f(lbm_handle h, int which, double* aos_padded);
 int lbm_download_macros(lbm_handle h, double* rho, double* ux, double* uy);
 int lbm_download_solid(lbm_handle h, unsigned char* mask);
