@@ -107,7 +107,7 @@ EXPORTS = [
     "lbm_set_kernel_variant", "lbm_device_count", "lbm_get_counters", "lbm_event_record", "lbm_event_elapsed",
     "lbm_bootstrap_env", "lbm_set_params", "lbm_snapshot_begin_slot", "lbm_snapshot_wait_slot", "lbm_allreduce", "lbm_gather_macros",
     "lbm_get_bulk_updates", "lbm_set_pass_depth", "lbm_set_force_mode", "lbm_snapshot_begin_slot2d", "lbm_host_register",
-    "lbm_host_unregister", "lbm_upload_f_next",
+    "lbm_host_unregister", "lbm_upload_f_next", "lbm_plan_passes",
 ]
 
 _lib = None
@@ -170,6 +170,7 @@ def load():
     L.lbm_host_register.argtypes = [C.c_void_p, C.c_size_t]
     L.lbm_host_unregister.argtypes = [C.c_void_p]
     L.lbm_upload_f_next.argtypes = [H, C.c_void_p]
+    L.lbm_plan_passes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, I, C.c_int]
     for name in EXPORTS:
         if name != "lbm_last_error":
             getattr(L, name).restype = C.c_int
@@ -394,6 +395,15 @@ class Solver:
         a = C.c_longlong()
         self._ck(load().lbm_get_bulk_updates(self._h, C.byref(a)))
         return a.value
+
+
+def plan_passes(iteration: int, n_steps: int, output_frequency: int, max_depth: int = 2, state_is_f_current: bool = False):
+    """The pass depths lbm_step(n_steps) launches from `iteration` on (host logic only, no device)."""
+    out = (C.c_int * max(n_steps, 1))()
+    n = load().lbm_plan_passes(iteration, n_steps, output_frequency, max_depth, 1 if state_is_f_current else 0, out, n_steps)
+    if n < 0:
+        raise LbmError(n, "bad arguments")
+    return list(out[:n])
 
 
 def device_count() -> int:

@@ -867,13 +867,16 @@ int step_tb(lbm_handle h, int depth, bool emit) {
 
 // How many iterations the next pass covers: as deep as the job allows, but an iteration whose collision is an
 // output step (forces are taken from ITS populations) must be the last one of its pass, and the first
-// iteration after initialise / upload stands alone.
-int next_depth(lbm_handle h, int remaining) {
-    if (!h->cur_is_next) return 1;
+// iteration after initialise / upload stands alone.  Pure: lbm_plan_passes exposes it to the CPU tests.
+int plan_depth(int iter, int remaining, int of, int max_depth, bool cur_is_next) {
+    if (!cur_is_next) return 1;
     int d = 1;
-    const int of = h->p.output_frequency;
-    while (d < h->tb_depth && d < remaining && !(of > 0 && (h->iter + d - 1) % of == 0)) ++d;
+    while (d < max_depth && d < remaining && !(of > 0 && (iter + d - 1) % of == 0)) ++d;
     return d;
+}
+
+int next_depth(lbm_handle h, int remaining) {
+    return plan_depth(h->iter, remaining, h->p.output_frequency, h->tb_depth, h->cur_is_next);
 }
 
 // One reference iteration (include/LBMSolver.h:49-58) as kernel launches.
@@ -1853,6 +1856,21 @@ int lbm_get_bulk_updates(lbm_handle h, long long* updates) {
     CHECK_H(h);
     if (updates) *updates = h->bulk_timed_updates;
     return LBM_OK;
+}
+
+int lbm_plan_passes(int iteration, int n_steps, int output_frequency, int max_depth, int state_is_f_current, int* depths,
+                    int max_passes) {
+    if (n_steps < 0 || max_depth < 1 || max_depth > TB_MAX_DEPTH || (max_passes > 0 && !depths)) return LBM_ERR_INVALID;
+    int n = 0;
+    bool cur_is_next = state_is_f_current == 0;
+    for (int k = 0; k < n_steps;) {
+        const int d = plan_depth(iteration + k, n_steps - k, output_frequency, max_depth, cur_is_next);
+        if (n < max_passes) depths[n] = d;
+        ++n;
+        k += d;
+        cur_is_next = true;
+    }
+    return n;
 }
 
 int lbm_set_force_mode(lbm_handle h, int mode) {
