@@ -107,7 +107,7 @@ EXPORTS = [
     "lbm_set_kernel_variant", "lbm_device_count", "lbm_get_counters", "lbm_event_record", "lbm_event_elapsed",
     "lbm_bootstrap_env", "lbm_set_params", "lbm_snapshot_begin_slot", "lbm_snapshot_wait_slot", "lbm_allreduce", "lbm_gather_macros",
     "lbm_get_bulk_updates", "lbm_set_pass_depth", "lbm_set_force_mode", "lbm_snapshot_begin_slot2d", "lbm_host_register",
-    "lbm_host_unregister", "lbm_upload_f_next", "lbm_plan_passes",
+    "lbm_host_unregister", "lbm_upload_f_next", "lbm_plan_passes", "lbm_selftest_division",
 ]
 
 _lib = None
@@ -170,6 +170,7 @@ def load():
     L.lbm_host_register.argtypes = [C.c_void_p, C.c_size_t]
     L.lbm_host_unregister.argtypes = [C.c_void_p]
     L.lbm_upload_f_next.argtypes = [H, C.c_void_p]
+    L.lbm_selftest_division.argtypes = [H, C.c_longlong, C.c_ulonglong, LL]
     L.lbm_plan_passes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, I, C.c_int]
     for name in EXPORTS:
         if name != "lbm_last_error":
@@ -385,6 +386,12 @@ class Solver:
     def set_pass_depth(self, d: int):
         """Iterations per temporally blocked pass (kernel variant 2): 1, 2 (default) or 3."""
         self._ck(load().lbm_set_pass_depth(self._h, d))
+
+    def selftest_division(self, n: int, seed: int = 1) -> int:
+        """Quotients of div_pair (the kernels' u = j / rho) that differ from the IEEE division on n random triples."""
+        bad = C.c_longlong()
+        self._ck(load().lbm_selftest_division(self._h, n, seed, C.byref(bad)))
+        return bad.value
 
     def set_force_mode(self, tree: int):
         """0: the reference's serial summation order (its bits); 1: fixed parallel tree (a few us, equal to rounding)."""

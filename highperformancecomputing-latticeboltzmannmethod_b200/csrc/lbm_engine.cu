@@ -1873,6 +1873,19 @@ int lbm_plan_passes(int iteration, int n_steps, int output_frequency, int max_de
     return n;
 }
 
+int lbm_selftest_division(lbm_handle h, long long n, unsigned long long seed, long long* mismatches) {
+    CHECK_H(h);
+    if (!mismatches || n < 0) return fail(h, LBM_ERR_INVALID, "bad argument");
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaMemsetAsync(h->d_maxbits, 0, sizeof(unsigned long long), h->stream));
+    CU(h, launch_selftest_div(seed, n, h->d_maxbits, h->stream));
+    unsigned long long bad = 0;
+    CU(h, cudaMemcpyAsync(&bad, h->d_maxbits, sizeof(bad), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    *mismatches = (long long)bad;
+    return LBM_OK;
+}
+
 int lbm_set_force_mode(lbm_handle h, int mode) {
     CHECK_H(h);
     if (mode != LBM_FORCES_ORDERED && mode != LBM_FORCES_TREE) return fail(h, LBM_ERR_INVALID, "force mode must be 0 or 1");

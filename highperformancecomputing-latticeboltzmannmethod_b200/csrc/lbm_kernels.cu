@@ -597,9 +597,55 @@ __global__ void __launch_bounds__(256) k_scatter(const long long* __restrict__ o
     if (f1) f1[off[k]] = val[k];
 }
 
+// Self-test of div_pair (lbm_cell.cuh) against the compiler's IEEE division, bit for bit, on pseudo-random operands:
+// densities near 1 and all over the exponent range (negative, zero, denormal, infinite, NaN included), numerators
+// from exactly zero (both signs) and denormals to beyond the stability limit.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+
+__device__ __forceinline__ double test_operand(unsigned long long h, int kind) {
+    const unsigned long long mant = h & 0x000FFFFFFFFFFFFFULL, sign = (h >> 63) << 63;
+    unsigned long long e;
+    switch (kind) {
+        case 0: e = 1022 + ((h >> 52) & 1); break;                  // [0.5, 2)
+        case 1: e = 1023 - 30 + ((h >> 52) % 48); break;            // 2^-30 .. 2^17
+        case 2: e = (h >> 52) & 0x7ff; break;                       // anything: denormals, inf, NaN
+        case 3: return __longlong_as_double((long long)sign);       // +-0
+        default: e = ((h >> 52) & 1) ? 1023 - 510 + ((h >> 53) % 20) : 1023 + 490 + ((h >> 53) % 20); break;  // the window's edges
+    }
+    return __longlong_as_double((long long)(sign | (e << 52) | mant));
+}
+
+__global__ void k_selftest_div(unsigned long long seed, long long n, unsigned long long* mismatches) {
+    unsigned long long bad = 0;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long h0 = mix64(seed + 3 * (unsigned long long)k), h1 = mix64(h0), h2 = mix64(h1);
+        const int mode = (int)(h0 % 10);
+        double den = test_operand(h0 >> 1, mode < 6 ? 0 : (mode < 8 ? 1 : (mode == 8 ? 2 : 4)));
+        if (mode < 7) den = fabs(den);
+        const double a = test_operand(h1, (int)((h1 >> 3) % 5)), b = test_operand(h2, (int)((h2 >> 3) % 5));
+        double qa, qb;
+        div_pair(a, b, den, qa, qb);
+        const double ra = a / den, rb = b / den;
+        const bool same_a = __double_as_longlong(qa) == __double_as_longlong(ra) || (qa != qa && ra != ra);
+        const bool same_b = __double_as_longlong(qb) == __double_as_longlong(rb) || (qb != qb && rb != rb);
+        bad += (same_a ? 0 : 1) + (same_b ? 0 : 1);
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace
+
+cudaError_t launch_selftest_div(unsigned long long seed, long long n, unsigned long long* mismatches, cudaStream_t s) {
+    k_selftest_div<<<148 * 8, 256, 0, s>>>(seed, n, mismatches);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_scatter(const long long* off, const double* val, int n, double* f0, double* f1, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;

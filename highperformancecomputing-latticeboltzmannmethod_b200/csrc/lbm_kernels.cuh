@@ -115,6 +115,8 @@ cudaError_t launch_maxvel(const double* ux, const double* uy, long long n, unsig
 // ... of the padded rows [row0, row0 + rows), `aos` pointing at the first of them (row0 a multiple of 32)
 cudaError_t launch_export_f(const ObserveArgs& o, int which, double* aos, int row0, int rows, cudaStream_t s);
 cudaError_t launch_import_f(const double* aos, double* f, const Layout& L, int row0, int rows, cudaStream_t s);
+// div_pair (lbm_cell.cuh) against the IEEE division on n pseudo-random operand triples; *mismatches += differing quotients.
+cudaError_t launch_selftest_div(unsigned long long seed, long long n, unsigned long long* mismatches, cudaStream_t s);
 // f0[off[k]] = f1[off[k]] = val[k]: caller-written f_next values of solid cells / ghost rows (lbm_upload_f_next).
 cudaError_t launch_scatter(const long long* off, const double* val, int n, double* f0, double* f1, cudaStream_t s);
 // Ghost ring of one buffer back to the convention (W/E domain-edge columns 0, everything else e).

@@ -239,6 +239,10 @@ int lbm_set_pass_depth(lbm_handle h, int depth); /* 1..3, default 2 (LBM_B200_TB
 int lbm_plan_passes(int iteration, int n_steps, int output_frequency, int max_depth, int state_is_f_current, int* depths,
                     int max_passes);
 int lbm_device_count(int* n);
+/* Self-test: the shared-reciprocal division the kernels use for u = j / rho (csrc/lbm_cell.cuh: div_pair) against the
+ * IEEE-754 division on n pseudo-random operand triples (densities near 1 and over the whole exponent range, numerators
+ * from +-0 and denormals to overflow, infinities and NaNs); *mismatches = quotients whose bits differ (must be 0). */
+int lbm_selftest_division(lbm_handle h, long long n, unsigned long long seed, long long* mismatches);
 
 #ifdef __cplusplus
 }

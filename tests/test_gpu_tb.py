@@ -152,3 +152,15 @@ def test_tree_force_reduction_equals_the_ordered_sum_to_rounding():
     scale = np.abs(want[:, 1:3]).max()
     assert np.abs(runs[1][:, 1:3] - want[:, 1:3]).max() <= 1e-14 * max(scale, 1.0)
     assert np.array_equal(runs[1][:, 0], want[:, 0])
+
+
+def test_shared_reciprocal_division_is_the_ieee_division():
+    """u = j / rho: the kernels divide both momentum components by the density through ONE refined reciprocal
+    (csrc/lbm_cell.cuh div_pair); bit for bit the IEEE quotient on 200 million random operand triples, special values
+    included."""
+    import lbm_b200
+
+    s = lbm_b200.Solver(lbm_b200.SimulationParams(nx=64, ny=32))
+    for seed in (1, 2, 3, 4):
+        assert s.selftest_division(50_000_000, seed) == 0
+    s.close()
