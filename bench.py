@@ -158,6 +158,36 @@ def smi_clocks_once(device: int) -> dict:
         return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable: %s" % e], "samples": 0}
 
 
+def bind_near_gpu(device: int):
+    """Pin this rank to the CPUs NVML lists as local to its GPU (its NUMA node) BEFORE any pinned host buffer is
+    allocated: first-touch then places the buffers next to the GPU's PCIe root, and the N ranks of a multi-GPU job stop
+    pulling each other's host traffic across the socket interconnect.  Returns (previous affinity, note); harmless where
+    every GPU reports the same CPU set."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = device
+        if vis:
+            try:
+                idx = int(vis.split(",")[device])
+            except ValueError:
+                idx = device
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        before = os.sched_getaffinity(0)
+        cpus &= before
+        if cpus and cpus != before:
+            os.sched_setaffinity(0, cpus)
+            return before, "rank pinned to the %d CPUs local to GPU %d (of %d)" % (len(cpus), idx, len(before))
+        return before, "GPU %d is local to every CPU of this process (%d)" % (idx, len(before))
+    except Exception as e:  # noqa: BLE001
+        return None, "no NVML CPU affinity (%s)" % type(e).__name__
+
+
 # ------------------------------------------------------------------------------------------------
 def measured_peak_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -425,6 +455,8 @@ def main():
     # ---------------------------------------------------------------- B200 arm
     import numpy as np
 
+    affinity_before, affinity_note = bind_near_gpu(local_rank)
+
     import lbm_b200  # raises if liblbm_b200.so is missing: there is no fallback path
 
     dist = None
@@ -612,6 +644,11 @@ def main():
 
     # ------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
     cpu = None
+    if affinity_before:
+        try:
+            os.sched_setaffinity(0, affinity_before)  # the reference gets every host core again
+        except OSError:
+            pass
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             v, cores, kind, sample, _ = run_reference(cfg, 20, 3, budget_s=30.0)
@@ -631,7 +668,8 @@ def main():
                                 world, max(info.pass_depth, 2) if info.kernel_variant == 2 else 1,
                                 "stored into the neighbour's memory by the step kernel itself (CUDA IPC peer memory over NVLink)"
                                 if info.halo_p2p else "by NCCL send/recv")) if world > 1 else "single GPU",
-                            "bytes_per_buffer": info.bytes_per_buffer, "deep_solid_cells_skipped": info.deep_solid_cells},
+                            "bytes_per_buffer": info.bytes_per_buffer, "deep_solid_cells_skipped": info.deep_solid_cells,
+                            "host_affinity": affinity_note},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clocks,
             "stable": bool(ok), "roofline_whole_step_frac": value * 1e6 * BYTES_PER_UPDATE / 1e9 / args.gpus / peak,
             ("multi_gpu_parity" if world > 1 else "parity_check"): parity,

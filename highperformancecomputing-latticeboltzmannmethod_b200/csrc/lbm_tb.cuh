@@ -2,24 +2,29 @@
 //
 // The A-B kernels of lbm_kernels.cu run at the HBM roofline of 144 B per update (9 fp64 loads + 9 fp64
 // stores); the only way past it is to do more than one update per trip through HBM.  One thread block
-// owns a strip of rows and marches along x through a chunk of columns.  At march step s
-//   stage 1   updates column s           from the source buffer in HBM        (reference iteration t)
-//   stage k   updates column s-(k-1)     from stage k-1's ring in SHARED MEMORY (iteration t+k-1)
-//   stage T   stores column s-(T-1)      to the destination buffer in HBM
+// owns a strip of rows and marches along x through a chunk of columns.  At march step s (the SKEWED march,
+// the default)
+//   stage 1   updates column s            from the source buffer in HBM          (reference iteration t)
+//   stage k   updates column s-2(k-1)     from stage k-1's ring in SHARED MEMORY (iteration t+k-1)
+//   stage T   stores column s-2(T-1)      to the destination buffer in HBM
 // so each population is read once and written once per T updates: 144/T B per update.  A stage's ring
-// holds its last four columns (a pull needs the three columns c-1, c, c+1; four slots make one
-// __syncthreads per stage and step enough).  Every stage is the complete reference iteration for its
+// holds its last four columns (a pull needs the three columns c-1, c, c+1).  Because stage k lags TWO
+// columns behind stage k-1, everything it reads was written in earlier steps: the stages of a step are
+// independent, stage 1's loads fly while the later stages compute, and one __syncthreads ends the step.
+// (The one-column-lag march -- stage k on column s-(k-1), a barrier between the stages, stage 1's loads
+// issued a step ahead into a second cell of registers -- is kept for A/B runs: LBM_B200_TB_SKEW=0.)
+// Every stage is the complete reference iteration for its
 // cells -- pull (include/LBMSolver.h:128-145), boundary rules in the reference's serial order
 // (:147-236), stability check (include/LBMGrid.h:285-317), BGK collision (:84-126) -- with the quirks
 // of SURVEY.md F3/F4 reproduced as VALUES of the intermediate state: solid cells are w, ghost rows are
 // eq(1,u_in,0), ghost columns at the physical inlet/outlet are 0, ghost columns at a slab interface
 // are computed from a halo of width T that the neighbouring GPU stored into this slab's memory.
 // The per-cell arithmetic is lbm_cell.cuh, so a pass of depth T is bit-identical to T single steps
-// (tests/test_tb_emulation.py runs THIS code on the host, thread for thread; tests/test_gpu_tb.py on
-// the GPU).
+// (tests/test_tb_emulation.py runs THIS code on the host, thread for thread, both marches;
+// tests/test_gpu_tb.py on the GPU).
 //
 // Redundant work: a strip of B threads yields B-4 rows (each stage needs one more row on either side
-// than the next), a chunk of XC columns costs XC + 2(T-1) stage-1 columns: ~3 % at B = 256, XC = 128.
+// than the next), a chunk of XC columns costs XC + 2(T-1) stage-1 columns: ~6 % at B = 128, XC = 64.
 //
 // Depth 1 is the plain fused step (pull + rules + collide in ONE launch, no fix-up kernel); it is what
 // multi-slab jobs use for the single steps between passes because it stores the same wide halo.
