@@ -4,31 +4,39 @@
 Contract (one JSON line on stdout from rank 0):
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
   N > 1 is launched by torchrun, one rank per GPU (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from
-  the environment); each rank owns one x-slab, the halo columns travel by NCCL send/recv.
+  the environment); each rank owns one x-slab, the halo of a pass is stored into the neighbouring
+  GPU's memory by the step kernel itself (CUDA IPC peer memory over NVLink; NCCL where unavailable).
 
 A "step" is one lattice update of the whole channel = one pass of Solver::run's loop body
 (reference include/LBMSolver.h:48-64): fused pull + boundary + collide, halo exchange, stability
-flag, and on every output_frequency-th step the momentum-exchange reduction.
+flag, and on every output_frequency-th step the momentum-exchange reduction.  The default kernels
+do TWO such steps per launch and per trip through HBM (temporal blocking, csrc/lbm_tb.cuh).
 
   value     MLUPS with the state resident in HBM, timed with CUDA events on the engine's compute
             stream, max over ranks.
   e2e       the same metric through the C-ABI with HOST buffers: one segment uploads the padded
             AoS f_current from pinned host memory (lbm_upload_f, H2D), runs max(K, 1000) steps
-            with Solver::run's observable behaviour (lbm_run: forces rows and the stability
-            verdict come back to the host) and downloads rho/ux/uy to pinned host memory
-            (lbm_download_macros, D2H) -- what Solver::initialise + run + write_final_results
-            amount to (the reference's own job is 120 000 steps per segment).  Timed with CUDA
-            events around the whole segment; the three parts are reported too.
-  roofline  bulk collide-stream kernel: 144 B per cell update (9 fp64 loads + 9 fp64 stores,
-            SURVEY.md section 8d) x cells per launch / average launch duration (CUDA events
-            around the bulk launch of every 8th step INSIDE the timed region), against MEASURED_PEAKS.json.
+            the way Solver::run does (lbm_run per output period: forces rows and the stability
+            verdict come back to the host; lbm_max_velocity after every output step) and downloads
+            rho/ux/uy to pinned host memory (lbm_download_macros, D2H) -- what Solver::initialise +
+            run + write_final_results amount to (the reference's own job is 120 000 steps per
+            segment).  Timed with CUDA events around the whole segment; the parts are reported too.
+  roofline  the dominant kernel: 144 B (9 fp64 loads + 9 fp64 stores) x the
+            cells a launch really moves through HBM / its average duration (CUDA events around the
+            launch of every 8th step INSIDE the timed region), against MEASURED_PEAKS.json: `frac`
+            is the honest traffic fraction; a pass of depth T updates every cell T times on that
+            trip, `frac_at_144B_per_update` = frac x T.
+  multi_gpu_parity / parity_check
+            BEFORE anything is timed: a seeded small case on the job's N slabs == one GPU running
+            the one-iteration kernels, bit for bit, and == the SHA-256 of the CPU oracle's result
+            committed under tests/golden/ (the oracle itself is not touched here).
   cpu_baseline  oracle/_ref/lbm_ref_fast (the unmodified reference headers built with the
             reference's own flags, all host cores) on a bounded sample of the same workload.
 
 Workloads (BASELINE.json configs): slab = weak-scaling cylinder flow, 4096 x 8192 cells per GPU
 (config 5; the default, the one the 1/2/4/8-GPU metric is quoted on); c3 = 8192 x 2048 cylinder
-flow at Re = 200; c4 = periodic obstacle-free 16384 x 16384; c1 = the reference's default
-2048 x 512 (L2-resident on a B200: reported, never the roofline evidence).
+flow at Re = 200; c4 = periodic obstacle-free 16384 x 16384 (adds physics_check: decay rate, mass);
+c1 = the reference's default 2048 x 512 (L2-resident on a B200: reported, never the roofline evidence).
 """
 from __future__ import annotations
 
@@ -400,7 +408,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="slab", choices=["slab", "c3", "c4", "c1"])
     ap.add_argument("--variant", type=int, default=None, help="bulk kernel variant (default: engine default)")
-    ap.add_argument("--aa", action="store_true", help="in-place AA variant: one population buffer (single GPU)")
+    ap.add_argument("--aa", action="store_true", help="in-place AA variant: one population buffer per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the seeded correctness check outside the timed regions")
