@@ -96,6 +96,7 @@ struct lbm_solver {
     int force_tree = 0;      // LBM_FORCES_TREE: fixed parallel reduction tree instead of the reference's serial order
     bool emit_last = false;  // lbm_run: the last pass of the call emits (the caller will look at the fields)
     int mask_lo = 0, mask_hi = 0;  // padded columns gx in [lo, hi) hold solid cells
+    int mask_ylo = 0, mask_yhi = 0;  // ... in rows [ylo, yhi)
     long long n_deep = 0;          // interior solid cells whose eight neighbours are solid (never touched)
     // lbm_download_f / lbm_upload_f: the padded AoS image crosses PCIe in row chunks through two staging buffers,
     // the copy of one chunk overlapping the transpose kernel of the other (no full-size third buffer)
@@ -275,6 +276,8 @@ int build_geometry(lbm_handle h) {
     std::vector<Link> links, links_rev, links_nat;
     h->mask_lo = L.lnx + 2 + Layout::XO;
     h->mask_hi = -Layout::XO;
+    h->mask_ylo = L.ny + 1;
+    h->mask_yhi = -1;
     for (int gx = -Layout::XO; gx < L.lnx + 2 + Layout::XO; ++gx)  // the wide ghost columns of lbm_tb.cuh included
         for (int y = -1; y <= L.ny; ++y) {
             const bool s = solid_global(L.x_start + gx - 1, y);
@@ -282,6 +285,8 @@ int build_geometry(lbm_handle h) {
             if (s) {
                 h->mask_lo = std::min(h->mask_lo, gx);
                 h->mask_hi = std::max(h->mask_hi, gx + 1);
+                h->mask_ylo = std::min(h->mask_ylo, y);
+                h->mask_yhi = std::max(h->mask_yhi, y + 1);
             }
             if (s && gx >= 1 && gx <= L.lnx && y >= 0 && y < L.ny) solids.push_back(make_int2(gx - 1, y));
         }
@@ -734,6 +739,8 @@ TbArgs tb_args(lbm_handle h, const double* src, double* dst, int bad_iter, int w
     a.mask = h->d_mask;
     a.mask_lo = h->mask_lo;
     a.mask_hi = h->mask_hi;
+    a.mask_ylo = h->mask_ylo;
+    a.mask_yhi = h->mask_yhi;
     a.west = h->west >= 0 ? TB_EDGE_HALO : (h->periodic_x ? TB_EDGE_WRAP : TB_EDGE_CONST);
     a.east = h->east >= 0 ? TB_EDGE_HALO : (h->periodic_x ? TB_EDGE_WRAP : TB_EDGE_CONST);
     a.periodic_y = h->periodic_y ? 1 : 0;

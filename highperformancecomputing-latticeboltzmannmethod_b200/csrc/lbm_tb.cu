@@ -166,7 +166,9 @@ int block_threads() {
 cudaError_t launch_tb(int depth, TbArgs a, bool p2p, cudaStream_t s) {
     const bool small = block_threads() == 128;
     tb_fill_offsets(a);
-    a.pf_dist = env_int("LBM_B200_TB_PF", 1);
+    static const int pf = env_int("LBM_B200_TB_PF", 1), fast = env_int("LBM_B200_TB_FAST", 1);
+    a.pf_dist = pf;
+    a.fast_lane = fast;
     switch (depth) {
         case 1: return small ? launch_forced<1, 128>(a, p2p, s) : launch_forced<1, 256>(a, p2p, s);
         case 2: return small ? launch_forced<2, 128>(a, p2p, s) : launch_forced<2, 256>(a, p2p, s);

@@ -55,6 +55,7 @@ struct TbArgs {
     BcArgs bc;
     const unsigned char* mask;  // padded, Layout indexing: 0 fluid, 1 solid, 2 solid with eight solid neighbours
     int mask_lo, mask_hi;       // slab columns [lo, hi) (ghost columns count) that may hold solid cells
+    int mask_ylo, mask_yhi;     // ... and the rows [ylo, yhi) they lie in: strips outside never look at the mask
     int west, east;             // TbEdge
     int periodic_y;
     int pull;   // depth 1 only: 0 = the first iteration after initialise / upload (collide f_current as it is)
@@ -72,6 +73,8 @@ struct TbArgs {
     long long ld_off[Q], st_off[Q], col_bytes;
     long long pf_off[Q];  // 8 (i*plane - c_ix*PY): the column segment population i is pulled from, 16-byte aligned
     int pf_dist;          // columns the L2 prefetch runs ahead of the loads (0: off)
+    long long plane_mul[5];  // k * 8 * plane bytes, k = 0..4 (the fast lane's pointer chains)
+    int fast_lane;        // 1: plain unmasked stretches of the skewed march take tb_fast_lane (0: A/B runs, tests)
 };
 
 inline void tb_fill_offsets(TbArgs& a) {
@@ -81,6 +84,7 @@ inline void tb_fill_offsets(TbArgs& a) {
         a.pf_off[i] = 8 * ((long long)i * a.L.plane - (long long)cxi(i) * a.L.PY);
     }
     a.col_bytes = 8 * (long long)a.L.PY;
+    for (int k = 0; k < 5; ++k) a.plane_mul[k] = 8 * (long long)k * a.L.plane;
 }
 
 // Keeps a per-thread pointer in its registers as ONE 64-bit value (the compiler would otherwise re-derive it from
@@ -111,6 +115,7 @@ LBM_HD int tb_opaque_int(int v) {
 // (the per-thread pointers are opaque 64-bit values, see tb_opaque: say "global" explicitly)
 #define TB_ST(ptr, v) asm volatile("st.global.f64 [%0], %1;" ::"l"(ptr), "d"(v) : "memory")
 #define TB_COLD __device__ __host__ __noinline__
+#define TB_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #else
 void tb_host_sync();
 void tb_host_flag(int* p, int v);
@@ -119,6 +124,7 @@ void tb_host_flag(int* p, int v);
 #define TB_FLAG(ptr, v) tb_host_flag((ptr), (v))
 #define TB_ST(ptr, v) (*reinterpret_cast<double*>(ptr) = (v))
 #define TB_COLD inline
+#define TB_PREFETCH_L2(p) ((void)(p))
 #endif
 
 LBM_HD int tb_wrap(int v, int n) {
@@ -464,6 +470,160 @@ LBM_HD void tb_step_skew(const TbArgs& a, const TbRow<T, B>& r, double* ring, in
     if (T > 1) TB_SYNC();
 }
 
+// The FAST LANE of the skewed march: march steps [s, s_end) whose T columns are all plain interior columns (see
+// tb_classify's PLAIN) without an obstacle cell, in a pass that stores populations and nothing else (no macro
+// emission) -- on the 4096 x 8192 slab that is 95 % of all steps.  Everything the general step decides per cell is
+// decided once per thread here: a thread either computes its row at stage k (act[k-1]) or does nothing (ghost rows
+// hold eq(1,u_in,0) in every ring slot from tb_thread's prologue on).  The per-thread pointers advance by one column
+// per step, so an access costs one 64-bit add of a constant-bank operand.  Same per-cell arithmetic, same order
+// (walls, stability check, moments, collision) as tb_finish: bit-identical by construction, and checked thread for
+// thread by the host emulation.
+// The populations of one cell of the fast lane, loaded / stored along a CHAIN of per-thread pointers: plane i+1 is
+// plane i plus ONE constant (8*plane bytes), so the loop needs two 64-bit constants instead of eighteen (which the
+// compiler would keep in uniform registers, run out of them and spill).  The pulled column x - c_ix is one of three
+// column pointers, the row shift -c_iy is the load's immediate offset.
+LBM_HD void tb_chain_load(const char* pl, long long col_bytes, const long long* pm, double f[Q]) {
+    const char* p0 = pl;                                 // c_ix =  0: populations 0, 2, 4
+    const char* pw = tb_opaque(pl - col_bytes);          // c_ix = +1: populations 1, 5, 8 come from column x - 1
+    const char* pe = tb_opaque(pl + col_bytes);          // c_ix = -1: populations 3, 6, 7 come from column x + 1
+    f[0] = TB_LD(reinterpret_cast<const double*>(p0), false);
+    pw = tb_opaque(pw + pm[1]);
+    f[1] = TB_LD(reinterpret_cast<const double*>(pw), false);
+    p0 = tb_opaque(p0 + pm[2]);
+    f[2] = TB_LD(reinterpret_cast<const double*>(p0) - 1, false);
+    pe = tb_opaque(pe + pm[3]);
+    f[3] = TB_LD(reinterpret_cast<const double*>(pe), false);
+    p0 = tb_opaque(p0 + pm[2]);
+    f[4] = TB_LD(reinterpret_cast<const double*>(p0) + 1, false);
+    pw = tb_opaque(pw + pm[4]);
+    f[5] = TB_LD(reinterpret_cast<const double*>(pw) - 1, false);
+    pe = tb_opaque(pe + pm[3]);
+    f[6] = TB_LD(reinterpret_cast<const double*>(pe) - 1, false);
+    pe = tb_opaque(pe + pm[1]);
+    f[7] = TB_LD(reinterpret_cast<const double*>(pe) + 1, false);
+    pw = tb_opaque(pw + pm[3]);
+    f[8] = TB_LD(reinterpret_cast<const double*>(pw) + 1, false);
+}
+LBM_HD void tb_chain_store(char* ps, long long plane_bytes, const double f[Q]) {
+    char* q = ps;
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+        TB_ST(q, f[i]);
+        if (i + 1 < Q) q = tb_opaque(q + plane_bytes);
+    }
+}
+
+// The per-cell work of the fast lane: walls, stability check, moments, collision -- tb_finish's sequence for a
+// fluid cell of a plain column.
+template <bool FORCED>
+LBM_HD bool tb_fast_cell(const TbArgs& a, bool strip_walls, bool wall_b, bool wall_t, double f[Q], Moments& mo) {
+    if (strip_walls) {  // (uniform over the block: two strips of the slab)
+        if (wall_b) wall_bottom(f);
+        if (wall_t) wall_top(f);
+    }
+    bool u = false;
+#pragma unroll
+    for (int i = 0; i < Q; ++i) u |= unstable_value(f[i]);
+    mo = moments(f);
+    if (FORCED)
+        bgk_forced(f, mo, a.tau_inv, a.Fx, a.Fy, f);
+    else
+        bgk(f, mo, a.tau_inv, f);
+    return u;
+}
+
+template <int T, int B, bool FORCED>
+LBM_HD void tb_fast_lane(const TbArgs& a, const TbRow<T, B>& r, double* ring, int s, const int s_end, bool bad[T]) {
+    bool act[T];
+#pragma unroll
+    for (int k = 0; k < T; ++k) act[k] = r.on[k] && r.row_kind == 1;
+    const long long plane_bytes = a.st_off[1];
+    // L2 prefetch, one 128-byte line per thread: thread j asks for line j % PF_LINES of population j / PF_LINES of the
+    // column the block pulls pf_dist steps from now (the nine segments of ~1 KB the bulk prefetch of the other steps
+    // covers with nine instructions of ONE thread -- here the work is one instruction in three of the four warps
+    // instead of fifty in the first one, which every barrier would wait for).
+    constexpr int PF_LINES = (B * 8 + 32 + 2 * 127) / 128;  // lines a segment of up to B + 4 rows can touch
+    static_assert(Q * PF_LINES <= B || B < 128, "one prefetch line per thread (the emulation's small blocks: a hint only)");
+    const char* pfp = nullptr;
+    if (r.pf_bytes > 0 && r.tid < Q * PF_LINES) {
+        const int pop = r.tid / PF_LINES, line = r.tid - pop * PF_LINES;
+        const int skew = (int)(reinterpret_cast<unsigned long long>(r.pf_seg) & 127);  // the segment starts mid-line
+        if (line * 128 < r.pf_bytes + skew)
+            pfp = tb_opaque(r.pf_seg - skew + a.pf_off[pop] + line * 128 + (long long)(s + a.pf_dist + 1 + Layout::XO) * a.col_bytes);
+    }
+    // stage 1 pulls column s; the last stage stores column s - 2(T-1)
+    const char* pl = tb_opaque(r.srow + (long long)(s + 1 + Layout::XO) * a.col_bytes);
+    char* ps = tb_opaque(r.drow + (long long)(s - 2 * (T - 1) + 1 + Layout::XO) * a.col_bytes);
+    double* const rt = ring + r.tid;
+    for (; s < s_end; ++s) {
+        if (pfp && s + a.pf_dist <= r.pf_last) TB_PREFETCH_L2(pfp);
+        // stage k works on column s - 2(k-1) while that lies in its range [x0 - (T-k), x1 + (T-k)) (uniform)
+        bool now[T];
+#pragma unroll
+        for (int k = 1; k <= T; ++k) {
+            const int c = s - 2 * (k - 1);
+            now[k - 1] = act[k - 1] && c >= r.x0 - (T - k) && c < r.x1 + (T - k);
+        }
+        double f1[Q];
+        if (now[0]) tb_chain_load(pl, a.col_bytes, a.plane_mul, f1);
+#pragma unroll
+        for (int k = T; k >= 2; --k) {
+            if (!now[k - 1]) continue;
+            const int c = s - 2 * (k - 1);
+            const double* g = rt + (k - 2) * (TB_SLOTS * Q * B);
+            const double* gw = g + ((c - 1) & (TB_SLOTS - 1)) * (Q * B);
+            const double* g0 = g + (c & (TB_SLOTS - 1)) * (Q * B);
+            const double* ge = g + ((c + 1) & (TB_SLOTS - 1)) * (Q * B);
+            double f[Q];
+            f[0] = g0[0 * B];
+            f[1] = gw[1 * B];
+            f[2] = g0[2 * B - 1];
+            f[3] = ge[3 * B];
+            f[4] = g0[4 * B + 1];
+            f[5] = gw[5 * B - 1];
+            f[6] = ge[6 * B - 1];
+            f[7] = ge[7 * B + 1];
+            f[8] = gw[8 * B + 1];
+            Moments mo;
+            bad[k - 1] |= tb_fast_cell<FORCED>(a, r.strip_walls, r.wall_b, r.wall_t, f, mo);
+            if (k < T) {
+                double* w = rt + (k - 1) * (TB_SLOTS * Q * B) + (c & (TB_SLOTS - 1)) * (Q * B);
+#pragma unroll
+                for (int i = 0; i < Q; ++i) w[i * B] = f[i];
+            } else {
+                if (a.m_rho) {  // (uniform; the last pass before an output only)
+                    const long long g = (long long)c * a.L.ny + r.y;
+                    a.m_rho[g] = mo.rho;
+                    a.m_ux[g] = mo.ux;
+                    a.m_uy[g] = mo.uy;
+                }
+                tb_chain_store(ps, plane_bytes, f);
+            }
+        }
+        if (now[0]) {
+            Moments mo;
+            bad[0] |= tb_fast_cell<FORCED>(a, r.strip_walls, r.wall_b, r.wall_t, f1, mo);
+            if (T > 1) {
+                double* w = rt + (s & (TB_SLOTS - 1)) * (Q * B);
+#pragma unroll
+                for (int i = 0; i < Q; ++i) w[i * B] = f1[i];
+            } else {
+                if (a.m_rho) {
+                    const long long g = (long long)s * a.L.ny + r.y;
+                    a.m_rho[g] = mo.rho;
+                    a.m_ux[g] = mo.ux;
+                    a.m_uy[g] = mo.uy;
+                }
+                tb_chain_store(ps, plane_bytes, f1);
+            }
+        }
+        pl = tb_opaque(pl + a.col_bytes);
+        ps = tb_opaque(ps + a.col_bytes);
+        if (pfp) pfp = tb_opaque(pfp + a.col_bytes);
+        if (T > 1) TB_SYNC();
+    }
+}
+
 // One thread of one block: `tid` in [0, B), rows of strip `strip`, columns of chunk `chunk`.
 // `ring` is the block's shared memory (TbShape::RING_DOUBLES doubles).
 template <int T, int B, bool FORCED, bool SKEW = true>
@@ -531,12 +691,40 @@ LBM_HD void tb_thread(const TbArgs& a, double* ring, int tid_, int strip_, int c
         if (r.edge) p1 = p0;  // the few slab-edge columns also feed the neighbour: general path
         r.pf_last = r.x1 + (T - 2) < lnx ? r.x1 + (T - 2) : lnx;  // the last column stage 1 loads
         // the columns s-2(T-1) .. s a step touches may hold obstacle cells iff they meet [mask_lo - 1, mask_hi - 1)
-        const int m0 = a.mask_lo - 1, m1 = a.mask_hi - 1 + 2 * (T - 1);  // steps s in [m0, m1) are masked
-        for (int s = s_first; s <= s_last; ++s) {
-            if (s >= p0 && s < p1)
-                tb_step_skew<T, B, FORCED, true>(a, r, ring, s, s >= m0 && s < m1, bad);
-            else
-                tb_step_skew<T, B, FORCED, false>(a, r, ring, s, true, bad);
+        int m0 = a.mask_lo - 1, m1 = a.mask_hi - 1 + 2 * (T - 1);  // steps s in [m0, m1) are masked
+        {
+            // ... for the strips whose rows meet the obstacle's rows (uniform over the block)
+            const int lo = strip * S::H - S::ROFF;
+            if (!a.periodic_y && (lo >= a.mask_yhi || lo + B <= a.mask_ylo)) m1 = m0;
+        }
+        // ghost rows: eq(1,u_in,0) in every ring slot, once, so that the fast lane never has to look at them (the
+        // other steps keep writing the same values); the first step's barrier publishes it
+        if (T > 1 && r.row_kind == 2) {
+#pragma unroll
+            for (int k = 1; k < T; ++k) {
+                if (!r.on[k - 1]) continue;
+                for (int slot = 0; slot < TB_SLOTS; ++slot)
+                    tb_ring_const<B>(ring + (k - 1) * (TB_SLOTS * Q * B) + slot * (Q * B) + r.tid, a, 2);
+            }
+        }
+        // The fast lane takes every step whose columns are plain and unmasked: in a chunk that touches neither slab
+        // edge that is the whole march (the stages switch themselves on and off at the chunk's ends), otherwise the
+        // steps [p0, p1) with every stage inside its range.
+        const bool fast = a.write && ((T > 1) || a.pull) && a.fast_lane;
+        int q0 = p0, q1 = p1;
+        if (!r.edge && r.x0 - (T - 1) >= c_lo && r.x1 + (T - 1) <= c_hi) { q0 = s_first; q1 = s_last + 1; }
+        if (!fast) q1 = q0;
+        int s = s_first;
+        while (s <= s_last) {
+            if (s >= q0 && s < q1 && !(s >= m0 && s < m1)) {
+                // up to the obstacle columns, or from behind them to the end of the stretch
+                const int e = (s < m0 && m0 < q1) ? m0 : q1;
+                tb_fast_lane<T, B, FORCED>(a, r, ring, s, e, bad);
+                s = e;
+                continue;
+            }
+            tb_step_skew<T, B, FORCED, false>(a, r, ring, s, true, bad);
+            ++s;
         }
     } else {
     // Stage k on column s - (k-1), stage 1's loads issued one step ahead into a second cell of registers.

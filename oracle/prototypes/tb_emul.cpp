@@ -33,6 +33,7 @@ using namespace lbm;
 namespace {
 
 bool g_skew = true;  // which march (lbm_tb.cuh) the emulation runs; tb_set_skew
+int g_fast = 1;      // ... and whether the skewed march takes its fast lane
 
 struct Slab {
     Layout L;
@@ -40,6 +41,24 @@ struct Slab {
     std::vector<unsigned char> mask;
     int cur = 0;
 };
+
+// The padded columns [lo, hi) that hold solid cells, as the engine's build_geometry hands them to the kernels
+// (an empty range when there is none): outside it the march skips the mask and may take its fast lane.
+void mask_range(const Slab& s, TbArgs& a) {
+    const Layout& L = s.L;
+    a.mask_lo = L.lnx + 2 + Layout::XO;
+    a.mask_hi = -Layout::XO;
+    a.mask_ylo = L.ny + 1;
+    a.mask_yhi = -1;
+    for (int gx = -Layout::XO; gx < L.lnx + 2 + Layout::XO; ++gx)
+        for (int y = -1; y <= L.ny; ++y)
+            if (s.mask[L.at(gx, y)]) {
+                a.mask_lo = gx < a.mask_lo ? gx : a.mask_lo;
+                a.mask_hi = gx + 1 > a.mask_hi ? gx + 1 : a.mask_hi;
+                a.mask_ylo = y < a.mask_ylo ? y : a.mask_ylo;
+                a.mask_yhi = y + 1 > a.mask_yhi ? y + 1 : a.mask_yhi;
+            }
+}
 
 // k_wrap of the engine: periodic edges keep wrapped copies in the ghost ring (x first, then y with the ghost
 // columns, so that the corners come out right).
@@ -154,7 +173,9 @@ void init_slab(Slab& s, int r, int world, const double* state, const unsigned ch
 
 extern "C" {
 
-void tb_set_skew(int on) { g_skew = on != 0; }
+// 0: the one-column-lag march; 1: the skewed march, every step on the general / lean step; 2: the skewed march with
+// its fast lane (what the device runs by default)
+void tb_set_skew(int on) { g_skew = on != 0; g_fast = on == 2; }
 
 // state:  global padded AoS [(gy*(nx+2)+gx)*9+i] (reference include/LBMGrid.h:105-107): a post-collision f_next
 //         (first_is_current = 0) or an f_current (first_is_current = 1: the first pass must have depth 1 and
@@ -195,8 +216,7 @@ int tb_emulate(double* state, const unsigned char* solid, int nx, int ny, double
             a.bc.outlet = (!per_x && r == world - 1) ? 1 : 0;
             a.bc.walls = per_y ? 0 : 1;
             a.mask = s.mask.data();
-            a.mask_lo = -Layout::XO;
-            a.mask_hi = lnx + 2 + Layout::XO;
+            mask_range(s, a);
             const bool has_w = r > 0 || (per_x && world > 1), has_e = r < world - 1 || (per_x && world > 1);
             a.west = has_w ? TB_EDGE_HALO : (per_x ? TB_EDGE_WRAP : TB_EDGE_CONST);
             a.east = has_e ? TB_EDGE_HALO : (per_x ? TB_EDGE_WRAP : TB_EDGE_CONST);
@@ -223,6 +243,7 @@ int tb_emulate(double* state, const unsigned char* solid, int nx, int ny, double
             }
             tb_fill_offsets(a);
             a.pf_dist = 1;
+            a.fast_lane = g_fast;
             run_pass(depth, B, a, chunks);
             if (!a.pull) {
                 // the engine's one-off launch after the first iteration: the buffer just read (an uploaded f_current may
@@ -297,8 +318,7 @@ int tbs_pass(void* h, int depth, int B, int xc, int edge_cols, int iter) {
     a.bc.outlet = p->rank == p->world - 1 ? 1 : 0;
     a.bc.walls = 1;
     a.mask = s.mask.data();
-    a.mask_lo = -Layout::XO;
-    a.mask_hi = p->lnx + 2 + Layout::XO;
+    mask_range(s, a);
     a.west = p->rank > 0 ? TB_EDGE_HALO : TB_EDGE_CONST;
     a.east = p->rank < p->world - 1 ? TB_EDGE_HALO : TB_EDGE_CONST;
     a.pull = (p->passes == 0 && p->first_is_current) ? 0 : 1;
@@ -313,6 +333,7 @@ int tbs_pass(void* h, int depth, int B, int xc, int edge_cols, int iter) {
     a.px.peer_dst_east = p->rank < p->world - 1 ? p->out_e.data() : nullptr;
     tb_fill_offsets(a);
     a.pf_dist = 1;
+    a.fast_lane = g_fast;
     run_pass(depth, B, a, chunks);
     if (!a.pull)
         for (int gx = 1; gx <= p->lnx; ++gx)
