@@ -10,7 +10,7 @@ Contract (one JSON line on stdout from rank 0):
 A "step" is one lattice update of the whole channel = one pass of Solver::run's loop body
 (reference include/LBMSolver.h:48-64): fused pull + boundary + collide, halo exchange, stability
 flag, and on every output_frequency-th step the momentum-exchange reduction.  The default kernels
-do TWO such steps per launch and per trip through HBM (temporal blocking, csrc/lbm_tb.cuh).
+do THREE such steps per launch and per trip through HBM (temporal blocking, csrc/lbm_tb.cuh).
 
   value     MLUPS with the state resident in HBM, timed with CUDA events on the engine's compute
             stream, max over ranks.

@@ -83,7 +83,7 @@ struct lbm_solver {
     // number of iterations between f[cur ^ 1] and f[cur] (the observers of rho / u want 1); the last stage
     // of a pass can emit the moments its collision read in the slab's native order (d_m*), valid for the
     // state after iteration macros_native_iter - 1.
-    int tb_depth = 2;
+    int tb_depth = 3;
     int lag = 1;
     double *d_mrho = nullptr, *d_mux = nullptr, *d_muy = nullptr;
     int macros_native_iter = -1;

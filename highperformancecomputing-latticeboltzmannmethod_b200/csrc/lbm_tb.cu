@@ -156,7 +156,7 @@ cudaError_t launch_forced(const TbArgs& a, bool p2p, cudaStream_t s) {
 int block_threads() {
     static const int b = [] {
         const int v = env_int("LBM_B200_TB_B", 128);
-        return v == 256 ? 256 : 128;
+        return v == 256 ? 256 : (v == 64 ? 64 : 128);
     }();
     return b;
 }
@@ -164,15 +164,15 @@ int block_threads() {
 }  // namespace
 
 cudaError_t launch_tb(int depth, TbArgs a, bool p2p, cudaStream_t s) {
-    const bool small = block_threads() == 128;
+    const int b = block_threads();
     tb_fill_offsets(a);
     static const int pf = env_int("LBM_B200_TB_PF", 1), fast = env_int("LBM_B200_TB_FAST", 1);
     a.pf_dist = pf;
     a.fast_lane = fast;
     switch (depth) {
-        case 1: return small ? launch_forced<1, 128>(a, p2p, s) : launch_forced<1, 256>(a, p2p, s);
-        case 2: return small ? launch_forced<2, 128>(a, p2p, s) : launch_forced<2, 256>(a, p2p, s);
-        case 3: return small ? launch_forced<3, 128>(a, p2p, s) : launch_forced<3, 256>(a, p2p, s);
+        case 1: return b == 128 ? launch_forced<1, 128>(a, p2p, s) : (b == 64 ? launch_forced<1, 64>(a, p2p, s) : launch_forced<1, 256>(a, p2p, s));
+        case 2: return b == 128 ? launch_forced<2, 128>(a, p2p, s) : (b == 64 ? launch_forced<2, 64>(a, p2p, s) : launch_forced<2, 256>(a, p2p, s));
+        case 3: return b == 128 ? launch_forced<3, 128>(a, p2p, s) : (b == 64 ? launch_forced<3, 64>(a, p2p, s) : launch_forced<3, 256>(a, p2p, s));
         default: return cudaErrorInvalidValue;
     }
 }
