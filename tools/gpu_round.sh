@@ -1,13 +1,14 @@
 # End-of-round check on one B200: the whole GPU suite, smoke, the judged bench lines, the other workloads, ncu evidence.
-# Usage (under gpurun): bash tools/gpu_round.sh
+# Usage (under gpurun): [WITH_REFERENCE=1] [WITH_AA=1] bash tools/gpu_round.sh
 python -m pytest tests -m gpu -q > gpurun_out/final_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/final_pytest_gpu.log | cut -c1-300
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 python bench.py > gpurun_out/final_bench_default.json 2> gpurun_out/final_bench_default.err; echo "bench rc=$?"
 python bench.py --steps 20 --warmup 5 > gpurun_out/final_bench_20.json 2> gpurun_out/final_bench_20.err; echo "bench20 rc=$?"
-python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/final_bench_reference.json 2> gpurun_out/final_bench_reference.err; echo "ref rc=$?"
+[ -n "$WITH_REFERENCE" ] && { python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/final_bench_reference.json 2> gpurun_out/final_bench_reference.err; echo "ref rc=$?"; }
 for wl in c3 c4 c1; do python bench.py --workload $wl --no-cpu-baseline $( [ $wl = c4 ] && echo "--no-e2e --steps 300" ) > gpurun_out/final_bench_$wl.json 2>/dev/null; echo "$wl rc=$?"; done
 python bench.py --variant 1 --no-cpu-baseline --no-e2e --steps 400 > gpurun_out/final_bench_variant1.json 2>/dev/null; echo "v1 rc=$?"
-python bench.py --aa --no-cpu-baseline --no-e2e --steps 400 > gpurun_out/final_bench_aa.json 2>/dev/null; echo "aa rc=$?"
+python bench.py --depth 2 --no-cpu-baseline --no-e2e --steps 400 > gpurun_out/final_bench_depth2.json 2>/dev/null; echo "depth2 rc=$?"
+[ -n "$WITH_AA" ] && { python bench.py --aa --no-cpu-baseline --no-e2e --steps 400 > gpurun_out/final_bench_aa.json 2>/dev/null; echo "aa rc=$?"; }
 python - <<'PY'
 import json, glob
 for f in sorted(glob.glob("gpurun_out/final_bench_*.json")):
