@@ -404,7 +404,7 @@ class Solver:
         return a.value
 
 
-def plan_passes(iteration: int, n_steps: int, output_frequency: int, max_depth: int = 2, state_is_f_current: bool = False):
+def plan_passes(iteration: int, n_steps: int, output_frequency: int, max_depth: int = 3, state_is_f_current: bool = False):
     """The pass depths lbm_step(n_steps) launches from `iteration` on (host logic only, no device)."""
     out = (C.c_int * max(n_steps, 1))()
     n = load().lbm_plan_passes(iteration, n_steps, output_frequency, max_depth, 1 if state_is_f_current else 0, out, n_steps)

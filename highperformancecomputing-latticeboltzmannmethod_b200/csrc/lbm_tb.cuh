@@ -116,6 +116,7 @@ LBM_HD int tb_opaque_int(int v) {
 #define TB_ST(ptr, v) asm volatile("st.global.f64 [%0], %1;" ::"l"(ptr), "d"(v) : "memory")
 #define TB_COLD __device__ __host__ __noinline__
 #define TB_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+#define TB_COUNT(which, n) ((void)0)
 #else
 void tb_host_sync();
 void tb_host_flag(int* p, int v);
@@ -125,6 +126,8 @@ void tb_host_flag(int* p, int v);
 #define TB_ST(ptr, v) (*reinterpret_cast<double*>(ptr) = (v))
 #define TB_COLD inline
 #define TB_PREFETCH_L2(p) ((void)(p))
+void tb_host_count(int which, int n);  // march steps a block took on the fast lane (0) / the general step (1)
+#define TB_COUNT(which, n) tb_host_count((which), (n))
 #endif
 
 LBM_HD int tb_wrap(int v, int n) {
@@ -719,10 +722,12 @@ LBM_HD void tb_thread(const TbArgs& a, double* ring, int tid_, int strip_, int c
             if (s >= q0 && s < q1 && !(s >= m0 && s < m1)) {
                 // up to the obstacle columns, or from behind them to the end of the stretch
                 const int e = (s < m0 && m0 < q1) ? m0 : q1;
+                if (tid == 0) TB_COUNT(0, e - s);
                 tb_fast_lane<T, B, FORCED>(a, r, ring, s, e, bad);
                 s = e;
                 continue;
             }
+            if (tid == 0) TB_COUNT(1, 1);
             tb_step_skew<T, B, FORCED, false>(a, r, ring, s, true, bad);
             ++s;
         }

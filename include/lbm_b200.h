@@ -231,7 +231,7 @@ int lbm_event_elapsed(lbm_handle h, int slot_a, int slot_b, float* ms);
  * All three give the same bits.  In a multi-slab job the variant / depth can only change before the first
  * iteration after lbm_initialise / lbm_upload_f. */
 int lbm_set_kernel_variant(lbm_handle h, int variant);
-int lbm_set_pass_depth(lbm_handle h, int depth); /* 1..3, default 2 (LBM_B200_TB_DEPTH) */
+int lbm_set_pass_depth(lbm_handle h, int depth); /* 1..3, default 3 (LBM_B200_TB_DEPTH) */
 /* The passes lbm_step(n_steps) launches from reference iteration `iteration` on (no device needed: pure host logic).
  * An iteration whose collision is an output step (iteration % output_frequency == 0: record_forces reads ITS
  * populations, LBMSolver.h:52-54) ends its pass; the first iteration after initialise / upload

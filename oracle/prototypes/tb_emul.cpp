@@ -20,7 +20,12 @@ namespace lbm {
 namespace {
 thread_local std::barrier<>* g_barrier = nullptr;
 std::mutex g_flag_mutex;
+long long g_steps[2] = {0, 0};
 }  // namespace
+void tb_host_count(int which, int n) {
+    std::lock_guard<std::mutex> lock(g_flag_mutex);
+    g_steps[which] += n;
+}
 void tb_host_sync() { g_barrier->arrive_and_wait(); }
 void tb_host_flag(int* p, int v) {
     std::lock_guard<std::mutex> lock(g_flag_mutex);
@@ -176,6 +181,12 @@ extern "C" {
 // 0: the one-column-lag march; 1: the skewed march, every step on the general / lean step; 2: the skewed march with
 // its fast lane (what the device runs by default)
 void tb_set_skew(int on) { g_skew = on != 0; g_fast = on == 2; }
+// march steps (per block) taken on the fast lane / on the general step since the last call; resets the counters
+void tb_step_counts(long long* fast, long long* general) {
+    *fast = lbm::g_steps[0];
+    *general = lbm::g_steps[1];
+    lbm::g_steps[0] = lbm::g_steps[1] = 0;
+}
 
 // state:  global padded AoS [(gy*(nx+2)+gx)*9+i] (reference include/LBMGrid.h:105-107): a post-collision f_next
 //         (first_is_current = 0) or an f_current (first_is_current = 1: the first pass must have depth 1 and

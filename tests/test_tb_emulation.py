@@ -147,3 +147,29 @@ def test_periodic_passes_are_self_consistent(emu, flags):
     for depths in ((2, 2, 2), (3, 3), (2, 1, 3)):
         got, _ = emulate(emu, case, state, solid, depths, flags=flags, B=16, xc=7)
         assert np.array_equal(got[1:-1, 1:-1], ref[1:-1, 1:-1]), depths
+
+
+def test_the_fast_lane_carries_the_plain_stretches():
+    """The skewed march hands every stretch of plain, unmasked columns to tb_fast_lane: on a channel whose cylinder
+    sits in one corner of the lattice that is most of the march (and none of it with the lane switched off), so the
+    parity cases above do exercise it."""
+    L = C.CDLL(LIB)
+    L.tb_emulate.restype = C.c_int
+    L.tb_emulate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
+                             C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    case = O.Case(nx=96, ny=64, cylinder_x=0.15, cylinder_y=0.2, cylinder_radius=0.1, output_frequency=5)
+    o = O.Oracle(case)
+    o.run(1)
+    src, solid = o.f_next.copy(), padded_solid(o, case)
+    o.run(3)
+    counts = {}
+    for mode in (2, 1):
+        L.tb_set_skew(mode)
+        fast, general = C.c_longlong(), C.c_longlong()
+        L.tb_step_counts(C.byref(fast), C.byref(general))  # reset
+        got, bad = emulate(L, case, src, solid, (3,), B=32, xc=16)
+        L.tb_step_counts(C.byref(fast), C.byref(general))
+        counts[mode] = (fast.value, general.value)
+        assert np.array_equal(got[1:-1, 1:-1], o.f_next[1:-1, 1:-1])
+    assert counts[1][0] == 0 and counts[1][1] == sum(counts[2])
+    assert counts[2][0] > 3 * counts[2][1], counts
