@@ -18,14 +18,14 @@ namespace {
 // job the blocks of chunks 0 and 1 (the slab-edge columns) run the peer-memory hand-shake around their
 // march: they are the first blocks of the grid, so the neighbours get their halo while the interior
 // chunks are still being worked on.
-template <int T, int B, bool FORCED, bool SKEW>
+template <int T, int B, bool FORCED, bool SKEW, bool FUSED>
 __device__ __forceinline__ void tb_kernel_body(const TbArgs& a, int p2p) {
     extern __shared__ double ring[];
     pdl_wait();
     pdl_release();
     const bool edge_block = p2p && blockIdx.y < 2;
     if (edge_block) p2p_block_begin(a.px);
-    tb_thread<T, B, FORCED, SKEW>(a, ring, threadIdx.x, blockIdx.x, blockIdx.y);
+    tb_thread<T, B, FORCED, SKEW, FUSED>(a, ring, threadIdx.x, blockIdx.x, blockIdx.y);
     if (edge_block) p2p_block_end(a.px, gridDim.x * 2);
 }
 
@@ -33,10 +33,10 @@ __device__ __forceinline__ void tb_kernel_body(const TbArgs& a, int p2p) {
 // computed): 128 registers, 512 threads = 16 warps per SM -- measured: ANY spill costs more than the warps it buys (96
 // registers / 20 warps: 42 800 MLUPS, 112 / 18: 53 300, 128 / 16: 65 800; the L1 left beside 148 KB of rings is
 // tiny).  The one-column-lag march fits 80 registers (768 threads); depth 3: 384 threads.
-template <int T, int B, bool FORCED, bool SKEW = true>
+template <int T, int B, bool FORCED, bool SKEW = true, bool FUSED = false>
 __global__ void __launch_bounds__(B, (T == 3 ? 384 : ((SKEW && T == 2) || T == 1 ? TB_SKEW_THREADS : 768)) / B)
     k_tb(const __grid_constant__ TbArgs a, int p2p) {
-    tb_kernel_body<T, B, FORCED, SKEW>(a, p2p);
+    tb_kernel_body<T, B, FORCED, SKEW, FUSED>(a, p2p);
 }
 
 // native [x*ny + y] -> interior row-major [y*lnx + x], 32 x 32 tiles through shared memory, with the
@@ -85,11 +85,12 @@ int env_int(const char* name, int dflt) {
     return v ? std::atoi(v) : dflt;
 }
 
-template <int T, int B, bool FORCED, bool SKEW = true>
+template <int T, int B, bool FORCED, bool SKEW = true, bool FUSED = false>
 cudaError_t launch_one(TbArgs a, bool p2p, cudaStream_t s) {
     using S = TbShape<T, B>;
-    auto kern = k_tb<T, B, FORCED, SKEW>;
-    const size_t smem = (size_t)S::RING_DOUBLES * sizeof(double);
+    auto kern = k_tb<T, B, FORCED, SKEW, FUSED>;
+    // (+ 16 bytes: with fused stages the last thread of a block reads one double past its ring row, unused)
+    const size_t smem = (size_t)S::RING_DOUBLES * sizeof(double) + (FUSED ? 16 : 0);
     static int slots = 0;  // resident blocks on the whole device, per instantiation
     if (!slots) {
         if (smem > 48 * 1024) {
@@ -150,6 +151,8 @@ cudaError_t launch_forced(const TbArgs& a, bool p2p, cudaStream_t s) {
     const bool forced = (a.Fx != 0.0 || a.Fy != 0.0);
     static const bool skew = env_int("LBM_B200_TB_SKEW", 1) != 0;
     if (T == 2 && !forced && !skew) return launch_one<T, B, false, false>(a, p2p, s);  // (the one-column-lag march, for A/B runs)
+    static const bool fused = env_int("LBM_B200_TB_FUSED", 0) != 0;
+    if (T == 3 && B == 128 && !forced && fused) return launch_one<T, B, false, true, true>(a, p2p, s);  // (experimental)
     return forced ? launch_one<T, B, true>(a, p2p, s) : launch_one<T, B, false>(a, p2p, s);
 }
 

@@ -627,9 +627,128 @@ LBM_HD void tb_fast_lane(const TbArgs& a, const TbRow<T, B>& r, double* ring, in
     }
 }
 
+// The fast lane with the stages T..2 FUSED (experimental, k_tb<..., FUSED = true>): their cells come from shared
+// memory, so all of them are available at once; their arithmetic is written side by side -- the moment sums of all
+// cells, ONE branch for all divisions, the collisions -- so that the double-precision dependency chains of T-1
+// independent cells interleave in one basic block (the kernel is bound by exactly those chains: ncu's stall_wait and
+// the fp64 pipe at 62 %).  Every thread computes (rows that are off at a stage work on whatever the ring holds,
+// nothing of it is stored or flagged), which removes the per-thread branches as well.  Only for steps in which every
+// stage lies inside its column range: the caller gives the chunk's first and last steps to tb_fast_lane.
+template <int T, int B, bool FORCED>
+LBM_HD void tb_fast_lane_fused(const TbArgs& a, const TbRow<T, B>& r, double* ring, int s, const int s_end, bool bad[T]) {
+    constexpr int K = T > 1 ? T - 1 : 1;  // fused cells: stage k = j + 2 is cell j
+    bool act[T];
+#pragma unroll
+    for (int k = 0; k < T; ++k) act[k] = r.on[k] && r.row_kind == 1;
+    const long long plane_bytes = a.st_off[1];
+    constexpr int PF_LINES = (B * 8 + 32 + 2 * 127) / 128;
+    const char* pfp = nullptr;
+    if (r.pf_bytes > 0 && r.tid < Q * PF_LINES) {
+        const int pop = r.tid / PF_LINES, line = r.tid - pop * PF_LINES;
+        const int skew = (int)(reinterpret_cast<unsigned long long>(r.pf_seg) & 127);
+        if (line * 128 < r.pf_bytes + skew)
+            pfp = tb_opaque(r.pf_seg - skew + a.pf_off[pop] + line * 128 + (long long)(s + a.pf_dist + 1 + Layout::XO) * a.col_bytes);
+    }
+    const char* pl = tb_opaque(r.srow + (long long)(s + 1 + Layout::XO) * a.col_bytes);
+    char* ps = tb_opaque(r.drow + (long long)(s - 2 * (T - 1) + 1 + Layout::XO) * a.col_bytes);
+    double* const rt = ring + r.tid;
+    for (; s < s_end; ++s) {
+        if (pfp && s + a.pf_dist <= r.pf_last) TB_PREFETCH_L2(pfp);
+        double f1[Q];
+        if (act[0]) tb_chain_load(pl, a.col_bytes, a.plane_mul, f1);
+        // ---- stages T..2, side by side ----
+        double f[K][Q], rho[K], mx[K], my[K];
+        Moments mo[K];
+        bool window = true;
+#pragma unroll
+        for (int j = K - 1; j >= 0; --j) {
+            const int c = s - 2 * (j + 1);
+            const double* g = rt + j * (TB_SLOTS * Q * B);
+            const double* gw = g + ((c - 1) & (TB_SLOTS - 1)) * (Q * B);
+            const double* g0 = g + (c & (TB_SLOTS - 1)) * (Q * B);
+            const double* ge = g + ((c + 1) & (TB_SLOTS - 1)) * (Q * B);
+            f[j][0] = g0[0 * B];
+            f[j][1] = gw[1 * B];
+            f[j][2] = g0[2 * B - 1];
+            f[j][3] = ge[3 * B];
+            f[j][4] = g0[4 * B + 1];
+            f[j][5] = gw[5 * B - 1];
+            f[j][6] = ge[6 * B - 1];
+            f[j][7] = ge[7 * B + 1];
+            f[j][8] = gw[8 * B + 1];
+        }
+        if (r.strip_walls) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                if (r.wall_b) wall_bottom(f[j]);
+                if (r.wall_t) wall_top(f[j]);
+            }
+        }
+#pragma unroll
+        for (int j = K - 1; j >= 0; --j) {
+            bool u = false;
+#pragma unroll
+            for (int i = 0; i < Q; ++i) u |= unstable_value(f[j][i]);
+            bad[j + 1] |= u && act[j + 1];
+            moment_sums(f[j], rho[j], mx[j], my[j]);
+            window = window && div_pair_window(mx[j], my[j], rho[j]);
+        }
+        if (window) {
+#pragma unroll
+            for (int j = K - 1; j >= 0; --j) {
+                mo[j].rho = rho[j];
+                div_pair_core(mx[j], my[j], rho[j], mo[j].ux, mo[j].uy);
+            }
+        } else {
+#pragma unroll
+            for (int j = K - 1; j >= 0; --j) {
+                mo[j].rho = rho[j];
+                div_pair(mx[j], my[j], rho[j], mo[j].ux, mo[j].uy);
+            }
+        }
+#pragma unroll
+        for (int j = K - 1; j >= 0; --j) {
+            if (FORCED)
+                bgk_forced(f[j], mo[j], a.tau_inv, a.Fx, a.Fy, f[j]);
+            else
+                bgk(f[j], mo[j], a.tau_inv, f[j]);
+        }
+#pragma unroll
+        for (int j = K - 1; j >= 0; --j) {
+            if (!act[j + 1]) continue;
+            const int c = s - 2 * (j + 1);
+            if (j + 2 < T) {
+                double* w = rt + (j + 1) * (TB_SLOTS * Q * B) + (c & (TB_SLOTS - 1)) * (Q * B);
+#pragma unroll
+                for (int i = 0; i < Q; ++i) w[i * B] = f[j][i];
+            } else {
+                if (a.m_rho) {  // (uniform; the last pass before an output only)
+                    const long long g = (long long)c * a.L.ny + r.y;
+                    a.m_rho[g] = mo[j].rho;
+                    a.m_ux[g] = mo[j].ux;
+                    a.m_uy[g] = mo[j].uy;
+                }
+                tb_chain_store(ps, plane_bytes, f[j]);
+            }
+        }
+        // ---- stage 1 (its loads have been flying meanwhile) ----
+        if (act[0]) {
+            Moments m1;
+            bad[0] |= tb_fast_cell<FORCED>(a, r.strip_walls, r.wall_b, r.wall_t, f1, m1);
+            double* w = rt + (s & (TB_SLOTS - 1)) * (Q * B);
+#pragma unroll
+            for (int i = 0; i < Q; ++i) w[i * B] = f1[i];
+        }
+        pl = tb_opaque(pl + a.col_bytes);
+        ps = tb_opaque(ps + a.col_bytes);
+        if (pfp) pfp = tb_opaque(pfp + a.col_bytes);
+        TB_SYNC();
+    }
+}
+
 // One thread of one block: `tid` in [0, B), rows of strip `strip`, columns of chunk `chunk`.
 // `ring` is the block's shared memory (TbShape::RING_DOUBLES doubles).
-template <int T, int B, bool FORCED, bool SKEW = true>
+template <int T, int B, bool FORCED, bool SKEW = true, bool FUSED = false>
 LBM_HD void tb_thread(const TbArgs& a, double* ring, int tid_, int strip_, int chunk_) {
     using S = TbShape<T, B>;
     const int tid = tb_opaque_int(tid_), strip = tb_opaque_int(strip_), chunk = tb_opaque_int(chunk_);
@@ -723,7 +842,22 @@ LBM_HD void tb_thread(const TbArgs& a, double* ring, int tid_, int strip_, int c
                 // up to the obstacle columns, or from behind them to the end of the stretch
                 const int e = (s < m0 && m0 < q1) ? m0 : q1;
                 if (tid == 0) TB_COUNT(0, e - s);
-                tb_fast_lane<T, B, FORCED>(a, r, ring, s, e, bad);
+                if constexpr (FUSED && T > 2) {
+                    // every stage inside its range for s in [p0, p1): those steps with the stages T..2 fused, the
+                    // chunk's first and last steps on the plain fast lane (one call site: the loop is not unrolled)
+                    const int f0 = s > p0 ? s : p0, f1 = e < p1 ? e : p1;
+                    const bool any = f0 < f1;
+#pragma unroll 1
+                    for (int seg = 0; seg < 3; ++seg) {
+                        const int to = !any ? e : (seg == 0 ? f0 : (seg == 1 ? f1 : e));
+                        if (s >= to) continue;
+                        if (seg == 1 && any) tb_fast_lane_fused<T, B, FORCED>(a, r, ring, s, to, bad);
+                        else tb_fast_lane<T, B, FORCED>(a, r, ring, s, to, bad);
+                        s = to;
+                    }
+                } else {
+                    tb_fast_lane<T, B, FORCED>(a, r, ring, s, e, bad);
+                }
                 s = e;
                 continue;
             }

@@ -39,6 +39,7 @@ namespace {
 
 bool g_skew = true;  // which march (lbm_tb.cuh) the emulation runs; tb_set_skew
 int g_fast = 1;      // ... and whether the skewed march takes its fast lane
+bool g_fused = false;  // ... with the stages T..2 fused (k_tb<..., FUSED = true>)
 
 struct Slab {
     Layout L;
@@ -97,7 +98,8 @@ void run_blocks(const TbArgs& a, int chunks) {
             for (int tid = 0; tid < B; ++tid)
                 th.emplace_back([&, tid] {
                     g_barrier = &bar;
-                    if (g_skew) tb_thread<T, B, false, true>(a, ring.data(), tid, strip, chunk);
+                    if (g_skew && g_fused) tb_thread<T, B, false, true, true>(a, ring.data(), tid, strip, chunk);
+                    else if (g_skew) tb_thread<T, B, false, true>(a, ring.data(), tid, strip, chunk);
                     else tb_thread<T, B, false, false>(a, ring.data(), tid, strip, chunk);
                 });
             for (auto& t : th) t.join();
@@ -179,8 +181,8 @@ void init_slab(Slab& s, int r, int world, const double* state, const unsigned ch
 extern "C" {
 
 // 0: the one-column-lag march; 1: the skewed march, every step on the general / lean step; 2: the skewed march with
-// its fast lane (what the device runs by default)
-void tb_set_skew(int on) { g_skew = on != 0; g_fast = on == 2; }
+// its fast lane (what the device runs by default); 3: ... and the stages T..2 fused
+void tb_set_skew(int on) { g_skew = on != 0; g_fast = on >= 2; g_fused = on == 3; }
 // march steps (per block) taken on the fast lane / on the general step since the last call; resets the counters
 void tb_step_counts(long long* fast, long long* general) {
     *fast = lbm::g_steps[0];

@@ -26,12 +26,12 @@ CASES = {
 }
 
 
-@pytest.fixture(scope="module", params=["skewed", "skewed_no_fast_lane", "one_column_lag"])
+@pytest.fixture(scope="module", params=["skewed", "skewed_fused", "skewed_no_fast_lane", "one_column_lag"])
 def emu(request):
     """The marches of lbm_tb.cuh: the skewed one (stage k two columns behind stage k-1, the default) with and without
-    its fast lane for plain stretches, and the one-column-lag one with its second cell of prefetched registers."""
+    its fast lane for plain stretches (and with the later stages of the fast lane fused), and the one-column-lag one with its second cell of prefetched registers."""
     L = C.CDLL(LIB)
-    L.tb_set_skew({"skewed": 2, "skewed_no_fast_lane": 1, "one_column_lag": 0}[request.param])
+    L.tb_set_skew({"skewed": 2, "skewed_fused": 3, "skewed_no_fast_lane": 1, "one_column_lag": 0}[request.param])
     L.tb_emulate.restype = C.c_int
     L.tb_emulate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
                              C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
