@@ -31,3 +31,10 @@ print("| opcode | per cell update | share of instructions | share of stall sampl
 print("|---|---:|---:|---:|")
 for o, v in count.most_common(28):
     print("| %s | %.2f | %.1f %% | %.1f %% |" % (o, v / per, 100.0 * v / tot, 100.0 * samples[o] / max(stot, 1)))
+
+hot = sorted(rows, key=lambda r: -int(r["# Samples"]))[:40]
+print("\n## The 40 SASS instructions that drew the most stall samples (of %d)\n" % stot)
+print("| address | instruction | executed (warps) | samples |")
+print("|---|---|---:|---:|")
+for r in hot:
+    print("| ...%s | `%s` | %s | %s |" % (r["Address"][-5:], " ".join(r["Source"].split()), r["Instructions Executed"], r["# Samples"]))
