@@ -2,6 +2,10 @@
 through the C-ABI against the pinned CPU oracle -- populations, f_current, rho / u (emitted by the pass, rebuilt by
 a store-less re-run of the pass, or derived from the previous buffer), forces rows, the stability verdict.
 Everything bit-identical: the per-cell arithmetic is the same code as every other kernel's."""
+import os
+import subprocess
+import sys
+
 import numpy as np
 import pytest
 
@@ -111,17 +115,18 @@ def test_periodic_modes_agree_with_the_single_step_kernels(flags):
                 assert np.array_equal(x, y)
 
 
-def test_full_size_slab_two_passes():
-    """BASELINE size (the 4096 x 8192 per-GPU slab): seeded random state, 1 + 2 + 2 iterations, every population of
+@pytest.mark.parametrize("depth", [2, 3])
+def test_full_size_slab_two_passes(depth):
+    """BASELINE size (the 4096 x 8192 per-GPU slab): seeded random state, 1 + T + T iterations, every population of
     every cell against the CPU oracle."""
     case = O.Case(nx=4096, ny=8192)
     state = util.random_state(case, 12)
-    s = make(case, 2)
+    s = make(case, depth)
     s.upload_f(state, 0)
     o = util.oracle_with_state(case, state)
     del state
-    s.step(5)
-    o.run(5)
+    s.step(1 + 2 * depth)
+    o.run(1 + 2 * depth)
     fn = s.f_next()
     assert np.array_equal(fn, o.f_next)
     del fn
@@ -164,3 +169,15 @@ def test_shared_reciprocal_division_is_the_ieee_division():
     for seed in (1, 2, 3, 4):
         assert s.selftest_division(50_000_000, seed) == 0
     s.close()
+
+
+def test_fused_later_stages_give_the_same_bits():
+    """k_tb<3,128,0,1,FUSED> (LBM_B200_TB_FUSED=1, read once per process: hence a child process): the parity cases of
+    this file with the arithmetic of stages 3 and 2 written side by side."""
+    env = dict(os.environ, LBM_B200_TB_FUSED="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-p", "no:cacheprovider", "-k",
+                        "test_passes_match_oracle_bit_for_bit or test_seeded_random_state or test_run_rows_and_macros"],
+                       env=env, capture_output=True, text=True, timeout=900,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert " passed" in r.stdout and "skipped" not in r.stdout.splitlines()[-1], r.stdout[-500:]
