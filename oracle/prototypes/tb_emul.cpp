@@ -40,6 +40,7 @@ namespace {
 bool g_skew = true;  // which march (lbm_tb.cuh) the emulation runs; tb_set_skew
 int g_fast = 1;      // ... and whether the skewed march takes its fast lane
 bool g_fused = false;  // ... with the stages T..2 fused (k_tb<..., FUSED = true>)
+double* g_sink[3] = {nullptr, nullptr, nullptr};  // tb_set_macro_sink
 
 struct Slab {
     Layout L;
@@ -183,6 +184,13 @@ extern "C" {
 // 0: the one-column-lag march; 1: the skewed march, every step on the general / lean step; 2: the skewed march with
 // its fast lane (what the device runs by default); 3: ... and the stages T..2 fused
 void tb_set_skew(int on) { g_skew = on != 0; g_fast = on >= 2; g_fused = on == 3; }
+// Where the LAST pass of the next tb_emulate call (world = 1) emits the moments its last stage's collisions read:
+// three arrays of nx*ny doubles in the slab's native order [x*ny + y] (TbArgs::m_rho / m_ux / m_uy); nullptr: off.
+void tb_set_macro_sink(double* rho, double* ux, double* uy) {
+    g_sink[0] = rho;
+    g_sink[1] = ux;
+    g_sink[2] = uy;
+}
 // march steps (per block) taken on the fast lane / on the general step since the last call; resets the counters
 void tb_step_counts(long long* fast, long long* general) {
     *fast = lbm::g_steps[0];
@@ -257,6 +265,11 @@ int tb_emulate(double* state, const unsigned char* solid, int nx, int ny, double
             tb_fill_offsets(a);
             a.pf_dist = 1;
             a.fast_lane = g_fast;
+            if (world == 1 && p == n_pass - 1 && g_sink[0]) {
+                a.m_rho = g_sink[0];
+                a.m_ux = g_sink[1];
+                a.m_uy = g_sink[2];
+            }
             run_pass(depth, B, a, chunks);
             if (!a.pull) {
                 // the engine's one-off launch after the first iteration: the buffer just read (an uploaded f_current may

@@ -173,3 +173,28 @@ def test_the_fast_lane_carries_the_plain_stretches():
         assert np.array_equal(got[1:-1, 1:-1], o.f_next[1:-1, 1:-1])
     assert counts[1][0] == 0 and counts[1][1] == sum(counts[2])
     assert counts[2][0] > 3 * counts[2][1], counts
+
+
+@pytest.mark.parametrize("depths", [(3,), (2, 3), (1,), (3, 2)])
+def test_the_last_pass_emits_the_moments_of_its_last_collision(emu, depths):
+    """TbArgs::m_rho / m_ux / m_uy (what lbm_run's last pass hands to k_macros_finish): rho, ux, uy exactly as the
+    reference's collision stores them (include/LBMSolver.h:112-114), from the general step and from the fast lane;
+    obstacle cells keep rho = 1, u = 0 (:260-261).  The inlet / outlet columns get their overrides later
+    (k_macros_finish, GPU tests): compared here without them."""
+    case = CASES["70x33"]
+    o = O.Oracle(case)
+    o.f_current[...] = random_f_current(case, 9)
+    o.run(1)
+    src, solid = o.f_next.copy(), padded_solid(o, case)
+    sink = [np.full(case.nx * case.ny, np.nan) for _ in range(3)]
+    emu.tb_set_macro_sink.argtypes = [C.c_void_p] * 3
+    emu.tb_set_macro_sink(*[a.ctypes.data for a in sink])
+    try:
+        got, bad = emulate(emu, case, src, solid, depths, B=32, xc=16)
+    finally:
+        emu.tb_set_macro_sink(None, None, None)
+    o.run(sum(depths))
+    assert np.array_equal(got[1:-1, 1:-1], o.f_next[1:-1, 1:-1])
+    for mine, want in zip(sink, (o.rho, o.ux, o.uy)):
+        mine = mine.reshape(case.nx, case.ny).T  # native [x*ny + y] -> [y, x]
+        assert np.array_equal(mine[:, 1:-1], np.asarray(want)[:, 1:-1])
